@@ -1,0 +1,141 @@
+"""ctypes binding of the C-ABI library declared in include/gg_raster.h.
+
+The product path has no CPU fallback: if `csrc/libgg_raster.so` is missing and cannot be built,
+or a call fails, a RuntimeError is raised."""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+import shutil
+import subprocess
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(CSRC, "libgg_raster.so")
+SOURCES = ["project.cu", "binning.cu", "blend_fwd.cu", "blend_bwd.cu", "preprocess_bwd.cu", "c_api.cu"]
+HEADERS = ["common.cuh", os.path.join("..", "..", "include", "gg_raster.h")]
+NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+_lock = threading.Lock()
+_lib = None
+
+
+class GGView(C.Structure):
+    _fields_ = [("num_gaussians", C.c_int32), ("sh_coeffs", C.c_int32), ("sh_degree", C.c_int32),
+                ("image_width", C.c_int32), ("image_height", C.c_int32),
+                ("tanfovx", C.c_float), ("tanfovy", C.c_float), ("scale_modifier", C.c_float),
+                ("prefiltered", C.c_int32), ("debug", C.c_int32)]
+
+
+class GGInputs(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in
+                ("means3D", "shs", "colors_precomp", "opacities", "scales", "rotations", "cov3D_precomp",
+                 "bg", "viewmatrix", "projmatrix", "campos")]
+
+
+def _needs_build() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    for f in SOURCES + HEADERS:
+        p = os.path.join(CSRC, f)
+        if os.path.exists(p) and os.path.getmtime(p) > t:
+            return True
+    return False
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/*.cu for sm_100a into csrc/libgg_raster.so (in-tree, so it travels to the GPU box)."""
+    if not force and not _needs_build():
+        return LIB_PATH
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise RuntimeError("gaussian-garments_b200: nvcc not found and libgg_raster.so is missing/stale")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + SOURCES
+    res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    return LIB_PATH
+
+
+def load():
+    """Load the library (building it first when sources are newer and nvcc is available)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if _needs_build():
+            try:
+                build()
+            except Exception as e:  # stale-but-present library is still usable on a box without nvcc
+                if not os.path.exists(LIB_PATH):
+                    raise RuntimeError(
+                        "gaussian-garments_b200: CUDA extension libgg_raster.so is missing and could not be "
+                        f"built ({e}); there is no CPU fallback") from e
+        lib = C.CDLL(LIB_PATH)
+        vp, i32, i64, sz = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
+        P = C.POINTER
+        lib.gg_abi_version.restype = C.c_int
+        lib.gg_version.restype = C.c_char_p
+        lib.gg_last_error.restype = C.c_char_p
+        lib.gg_launch_count.restype = C.c_int64
+        lib.gg_launch_count.argtypes = [i32]
+        lib.gg_forward_workspace_bytes.argtypes = [P(GGView), P(sz), P(sz), P(sz)]
+        lib.gg_instance_workspace_bytes.argtypes = [i64, P(sz), P(sz)]
+        lib.gg_backward_workspace_bytes.argtypes = [P(GGView), P(sz)]
+        lib.gg_forward_project.argtypes = [P(GGView), P(GGInputs), vp, vp, vp, vp, i32, vp]
+        lib.gg_forward_color.argtypes = [P(GGView), P(GGInputs), vp, vp, i32, vp]
+        lib.gg_forward_render.argtypes = [P(GGView), P(GGInputs), vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, i32, vp]
+        lib.gg_backward.argtypes = [P(GGView), P(GGInputs), vp, vp, i64, vp, vp, vp] + [vp] * 11 + [i32, vp]
+        lib.gg_mark_visible.argtypes = [C.c_int32, vp, vp, vp, vp, i32, vp]
+        lib.gg_debug_read_geom.argtypes = [P(GGView), vp, vp, vp, vp, vp, vp, i32, vp]
+        lib.gg_kernel_timing.argtypes = [i32]
+        lib.gg_kernel_count.restype = C.c_int
+        lib.gg_kernel_name.restype = C.c_char_p
+        lib.gg_kernel_name.argtypes = [i32]
+        lib.gg_kernel_times.argtypes = [P(C.c_float)]
+        for name in ("gg_forward_workspace_bytes", "gg_instance_workspace_bytes", "gg_backward_workspace_bytes",
+                     "gg_forward_project", "gg_forward_color", "gg_forward_render", "gg_backward",
+                     "gg_mark_visible", "gg_debug_read_geom", "gg_kernel_timing", "gg_kernel_times"):
+            getattr(lib, name).restype = C.c_int
+        if lib.gg_abi_version() != 1:
+            raise RuntimeError("gaussian-garments_b200: libgg_raster.so ABI mismatch")
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = load().gg_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"gaussian-garments_b200: {what} failed (code {rc}): {msg}")
+
+
+EXPORTED_SYMBOLS = [
+    "gg_abi_version", "gg_version", "gg_last_error", "gg_launch_count", "gg_forward_workspace_bytes",
+    "gg_instance_workspace_bytes", "gg_backward_workspace_bytes", "gg_forward_project", "gg_forward_color",
+    "gg_forward_render", "gg_backward", "gg_mark_visible", "gg_debug_read_geom", "gg_kernel_timing",
+    "gg_kernel_count", "gg_kernel_name", "gg_kernel_times",
+]
+
+
+def kernel_timing(enable: bool):
+    check(load().gg_kernel_timing(1 if enable else 0), "gg_kernel_timing")
+
+
+def kernel_times() -> dict:
+    lib = load()
+    n = lib.gg_kernel_count()
+    buf = (C.c_float * n)()
+    check(lib.gg_kernel_times(buf), "gg_kernel_times")
+    return {lib.gg_kernel_name(i).decode(): float(buf[i]) for i in range(n) if buf[i] >= 0}
+
+
+def launch_count(reset: bool = False) -> int:
+    return int(load().gg_launch_count(1 if reset else 0))

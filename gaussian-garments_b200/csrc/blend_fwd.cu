@@ -1,0 +1,125 @@
+// blend_fwd.cu -- per-tile front-to-back alpha blending.
+//
+// One CTA (256 threads = 16x16 pixels) per tile.  The tile's depth-sorted packed records are
+// three contiguous float4 runs, streamed into shared memory by 1-D bulk TMA (cp.async.bulk,
+// SASS UBLKCP) through a 3-stage mbarrier ring: one elected thread arms a stage with
+// expect_tx and issues three bulk copies; all threads wait on the stage's phase parity, read the
+// records as shared-memory broadcasts, and a __syncthreads_count both recycles the stage and
+// detects "every pixel saturated" for the early exit.
+// A warp covers an 8x4 pixel block (not 16x2) so a small splat touches fewer warps.
+#include "common.cuh"
+
+namespace gg {
+
+constexpr int FWD_BATCH = 128;
+constexpr int FWD_STAGES = 3;
+
+__global__ void __launch_bounds__(TILE_PIX)
+blend_fwd_kernel(const uint32_t* __restrict__ tile_offset, const float4* __restrict__ p0,
+                 const float4* __restrict__ p1, const float4* __restrict__ p2, uint32_t capacity, int W, int H, int gx,
+                 const float* __restrict__ bg, float* __restrict__ out_color, float* __restrict__ out_depth,
+                 float* __restrict__ out_alpha, uint32_t* __restrict__ n_contrib, float* __restrict__ final_T) {
+    __shared__ __align__(128) float4 s0[FWD_STAGES][FWD_BATCH];
+    __shared__ __align__(128) float4 s1[FWD_STAGES][FWD_BATCH];
+    __shared__ __align__(128) float4 s2[FWD_STAGES][FWD_BATCH];
+    __shared__ __align__(8) uint64_t full[FWD_STAGES];
+
+    const uint32_t tile = blockIdx.x;
+    const int tx = tile % gx, ty = tile / gx;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int px = tx * TILE + (warp & 1) * 8 + (lane & 7);
+    const int py = ty * TILE + (warp >> 1) * 4 + (lane >> 3);
+    const bool inside = px < W && py < H;
+    const float fx = (float)px, fy = (float)py;
+
+    const uint32_t off = tile_offset[tile];
+    uint32_t n = tile_offset[tile + 1] - off;
+    if (off + n > capacity) n = 0;
+    const int nb = (n + FWD_BATCH - 1) / FWD_BATCH;
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < FWD_STAGES; s++) mbar_init(&full[s], 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](int b) {   // thread 0 only
+        const int st = b % FWD_STAGES;
+        const uint32_t cnt = min((uint32_t)FWD_BATCH, n - (uint32_t)b * FWD_BATCH);
+        const uint32_t bytes = cnt * 16u;
+        const size_t src = (size_t)off + (size_t)b * FWD_BATCH;
+        mbar_arrive_expect_tx(&full[st], 3u * bytes);
+        bulk_g2s(&s0[st][0], p0 + src, bytes, &full[st]);
+        bulk_g2s(&s1[st][0], p1 + src, bytes, &full[st]);
+        bulk_g2s(&s2[st][0], p2 + src, bytes, &full[st]);
+    };
+    if (threadIdx.x == 0)
+        for (int b = 0; b < nb && b < FWD_STAGES; b++) issue(b);
+
+    float T = 1.f, C0 = 0.f, C1 = 0.f, C2 = 0.f, Dp = 0.f, Ac = 0.f;
+    uint32_t last = 0;
+    bool done = !inside;
+    int b = 0;
+    for (; b < nb; b++) {
+        const int st = b % FWD_STAGES;
+        mbar_wait(&full[st], (uint32_t)(b / FWD_STAGES) & 1u);
+        if (!done) {
+            const int cnt = min(FWD_BATCH, (int)n - b * FWD_BATCH);
+            for (int j = 0; j < cnt; j++) {
+                const float4 a = s0[st][j];
+                const float4 c = s1[st][j];
+                const float dx = a.x - fx, dy = a.y - fy;
+                const float power = -0.5f * (a.z * dx * dx + c.x * dy * dy) - a.w * dx * dy;
+                if (power > 0.f) continue;
+                const float alpha = fminf(ALPHA_MAX, c.y * __expf(power));
+                if (alpha < ALPHA_MIN) continue;
+                const float test_T = T * (1.f - alpha);
+                if (test_T < T_STOP) {
+                    done = true;
+                    break;
+                }
+                const float w = alpha * T;
+                const float4 col = s2[st][j];
+                C0 += col.x * w;
+                C1 += col.y * w;
+                C2 += col.z * w;
+                Dp += c.z * w;
+                Ac += w;
+                T = test_T;
+                last = (uint32_t)(b * FWD_BATCH + j + 1);
+            }
+        }
+        const int n_done = __syncthreads_count(done);   // also: everyone has finished reading stage st
+        if (n_done == TILE_PIX) break;
+        if (threadIdx.x == 0 && b + FWD_STAGES < nb) issue(b + FWD_STAGES);
+    }
+    // drain bulk copies that were issued but never consumed (early exit) before the CTA retires
+    if (threadIdx.x == 0 && b < nb) {
+        for (int bb = b + 1; bb < nb && bb < b + FWD_STAGES; bb++)
+            mbar_wait(&full[bb % FWD_STAGES], (uint32_t)(bb / FWD_STAGES) & 1u);
+    }
+
+    if (inside) {
+        const size_t P = (size_t)W * H, pid = (size_t)py * W + px;
+        out_color[pid] = C0 + T * bg[0];
+        out_color[P + pid] = C1 + T * bg[1];
+        out_color[2 * P + pid] = C2 + T * bg[2];
+        out_depth[pid] = Dp;
+        out_alpha[pid] = Ac;
+        n_contrib[pid] = last;
+        final_T[pid] = T;
+    }
+}
+
+int launch_blend_fwd(const gg_view& v, const gg_inputs& in, const TileWS& t, const RecordWS& r, const ImageWS& img,
+                     uint32_t capacity, float* out_color, float* out_depth, float* out_alpha, cudaStream_t s) {
+    const int gx = (v.image_width + TILE - 1) / TILE, gy = (v.image_height + TILE - 1) / TILE;
+    const int T = gx * gy;
+    if (T == 0) return 0;
+    blend_fwd_kernel<<<T, TILE_PIX, 0, s>>>(t.offset, r.p0, r.p1, r.p2, capacity, v.image_width, v.image_height, gx,
+                                            in.bg, out_color, out_depth, out_alpha, img.n_contrib, img.final_T);
+    return 1;
+}
+
+}  // namespace gg

@@ -1,0 +1,310 @@
+// c_api.cu -- extern "C" boundary (include/gg_raster.h).  Argument validation, workspace
+// carving, launch sequencing, error reporting.  No allocation, no global mutable state.
+#include <atomic>
+#include <cstdio>
+#include <mutex>
+#include <cstring>
+#include "common.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+// profiling facilities (off by default).  Process-wide because autograd runs backward on a
+// worker thread: launch counts and per-kernel events must be visible from the caller's thread.
+std::atomic<int64_t> g_launches{0};
+
+enum KernelSlot { K_PROJECT = 0, K_SCAN, K_SHCOLOR, K_EMIT, K_SORTPACK, K_BLENDFWD, K_BLENDBWD, K_PREBWD, K_COUNT };
+const char* const kKernelNames[K_COUNT] = {"project", "tile_scan", "sh_color", "emit", "sort_pack",
+                                           "blend_fwd", "blend_bwd", "preprocess_bwd"};
+std::atomic<int> g_timing{0};
+std::mutex g_timing_mu;
+cudaEvent_t g_ev[K_COUNT][2];
+bool g_ev_made = false;
+bool g_ev_used[K_COUNT] = {false};
+
+struct ScopedKernelTimer {
+    int slot;
+    cudaStream_t s;
+    bool on;
+    ScopedKernelTimer(int slot_, cudaStream_t s_) : slot(slot_), s(s_), on(g_timing.load() != 0) {
+        if (on) {
+            std::lock_guard<std::mutex> lk(g_timing_mu);
+            cudaEventRecord(g_ev[slot][0], s);
+        }
+    }
+    ~ScopedKernelTimer() {
+        if (on) {
+            std::lock_guard<std::mutex> lk(g_timing_mu);
+            cudaEventRecord(g_ev[slot][1], s);
+            g_ev_used[slot] = true;
+        }
+    }
+};
+
+int fail(int code, const char* fmt, const char* what = "") {
+    snprintf(g_err, sizeof(g_err), fmt, what);
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* where) {
+    snprintf(g_err, sizeof(g_err), "%s: %s (%s)", where, cudaGetErrorString(e), cudaGetErrorName(e));
+    return (int)e;
+}
+#define GG_CUDA(call)                                         \
+    do {                                                      \
+        cudaError_t _e = (call);                              \
+        if (_e != cudaSuccess) return cuda_fail(_e, #call);   \
+    } while (0)
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int check_view(const gg_view* v) {
+    if (!v) return fail(GG_E_BADARG, "view is NULL");
+    if (v->num_gaussians < 0 || v->image_width < 0 || v->image_height < 0) return fail(GG_E_BADARG, "negative size in view");
+    if (v->sh_degree < 0 || v->sh_degree > 3) return fail(GG_E_BADARG, "sh_degree must be in 0..3");
+    if (v->image_width > 65535 * GG_TILE || v->image_height > 65535 * GG_TILE) return fail(GG_E_BADARG, "image too large");
+    return 0;
+}
+
+int check_inputs(const gg_view* v, const gg_inputs* in) {
+    if (!in) return fail(GG_E_BADARG, "inputs is NULL");
+    if (!in->bg || !in->viewmatrix || !in->projmatrix || !in->campos) return fail(GG_E_BADARG, "bg/viewmatrix/projmatrix/campos must be non-NULL");
+    if (v->num_gaussians == 0) return 0;
+    if (!in->means3D || !in->opacities) return fail(GG_E_BADARG, "means3D/opacities must be non-NULL");
+    if ((in->shs == nullptr) == (in->colors_precomp == nullptr)) return fail(GG_E_BADARG, "provide exactly one of shs / colors_precomp");
+    const bool sr = in->scales && in->rotations;
+    if (sr == (in->cov3D_precomp != nullptr) || (!sr && (in->scales || in->rotations)))
+        return fail(GG_E_BADARG, "provide exactly one of (scales, rotations) / cov3D_precomp");
+    if (in->shs && v->sh_coeffs < (v->sh_degree + 1) * (v->sh_degree + 1)) return fail(GG_E_BADARG, "sh_coeffs < (sh_degree+1)^2");
+    if (in->shs && v->sh_coeffs > 16) return fail(GG_E_BADARG, "sh_coeffs > 16 (degree <= 3) not supported");
+    if (in->rotations && !aligned16(in->rotations)) return fail(GG_E_ALIGN, "rotations not 16-byte aligned");
+    if (in->shs && v->sh_coeffs == 16 && !aligned16(in->shs)) return fail(GG_E_ALIGN, "shs not 16-byte aligned");
+    return 0;
+}
+
+int after_launch(const gg_view* v, cudaStream_t s, const char* where) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, where);
+    if (v && v->debug) {
+        e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) return cuda_fail(e, where);
+    }
+    return 0;
+}
+#define GG_AFTER(where)                                 \
+    do {                                                \
+        int _rc = after_launch(view, s, where);         \
+        if (_rc) return _rc;                            \
+    } while (0)
+
+}  // namespace
+
+using namespace gg;
+
+extern "C" {
+
+int gg_abi_version(void) { return GG_ABI_VERSION; }
+const char* gg_version(void) { return "gg_raster 0.1.0 (sm_100a)"; }
+const char* gg_last_error(void) { return g_err; }
+int64_t gg_launch_count(int reset) {
+    const int64_t v = g_launches.load();
+    if (reset) g_launches.store(0);
+    return v;
+}
+
+int gg_kernel_timing(int enable) {
+    std::lock_guard<std::mutex> lk(g_timing_mu);
+    if (enable && !g_ev_made) {
+        for (int k = 0; k < K_COUNT; k++)
+            for (int j = 0; j < 2; j++) GG_CUDA(cudaEventCreate(&g_ev[k][j]));
+        g_ev_made = true;
+    }
+    for (int k = 0; k < K_COUNT; k++) g_ev_used[k] = false;
+    g_timing.store(enable ? 1 : 0);
+    return 0;
+}
+
+int gg_kernel_count(void) { return K_COUNT; }
+const char* gg_kernel_name(int slot) { return (slot >= 0 && slot < K_COUNT) ? kKernelNames[slot] : ""; }
+
+int gg_kernel_times(float* ms_out) {
+    if (!ms_out) return fail(GG_E_BADARG, "ms_out is NULL");
+    std::lock_guard<std::mutex> lk(g_timing_mu);
+    for (int k = 0; k < K_COUNT; k++) {
+        ms_out[k] = -1.f;
+        if (!g_ev_made || !g_ev_used[k]) continue;
+        GG_CUDA(cudaEventSynchronize(g_ev[k][1]));
+        float ms = 0.f;
+        GG_CUDA(cudaEventElapsedTime(&ms, g_ev[k][0], g_ev[k][1]));
+        ms_out[k] = ms;
+    }
+    return 0;
+}
+
+int gg_forward_workspace_bytes(const gg_view* view, size_t* geom_bytes, size_t* tile_bytes, size_t* image_bytes) {
+    if (int rc = check_view(view)) return rc;
+    const int64_t gx = (view->image_width + TILE - 1) / TILE, gy = (view->image_height + TILE - 1) / TILE;
+    if (geom_bytes) *geom_bytes = geom_layout(nullptr, view->num_gaussians > 0 ? view->num_gaussians : 1, nullptr);
+    if (tile_bytes) *tile_bytes = tile_layout(nullptr, gx * gy, nullptr);
+    if (image_bytes) *image_bytes = image_layout(nullptr, (int64_t)view->image_width * view->image_height, nullptr);
+    return 0;
+}
+
+int gg_instance_workspace_bytes(int64_t num_rendered, size_t* key_bytes, size_t* record_bytes) {
+    if (num_rendered < 0 || num_rendered > 0xfffffff0ll) return fail(GG_E_BADARG, "num_rendered out of range");
+    if (key_bytes) *key_bytes = align_up((size_t)(num_rendered > 0 ? num_rendered : 1) * 8);
+    if (record_bytes) *record_bytes = record_layout(nullptr, num_rendered, nullptr);
+    return 0;
+}
+
+int gg_backward_workspace_bytes(const gg_view* view, size_t* accum_bytes) {
+    if (int rc = check_view(view)) return rc;
+    if (accum_bytes) *accum_bytes = accum_layout(nullptr, view->num_gaussians, nullptr);
+    return 0;
+}
+
+int gg_forward_project(const gg_view* view, const gg_inputs* in, void* geom_ws, void* tile_ws, int32_t* radii,
+                       uint32_t* num_rendered_host, int device, void* stream) {
+    if (int rc = check_view(view)) return rc;
+    if (int rc = check_inputs(view, in)) return rc;
+    if (!geom_ws || !tile_ws || (!radii && view->num_gaussians > 0)) return fail(GG_E_BADARG, "workspace / radii is NULL");
+    GG_CUDA(cudaSetDevice(device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const int gx = (view->image_width + TILE - 1) / TILE, gy = (view->image_height + TILE - 1) / TILE;
+    const int T = gx * gy;
+    GeomWS g;
+    TileWS t;
+    geom_layout(geom_ws, view->num_gaussians > 0 ? view->num_gaussians : 1, &g);
+    tile_layout(tile_ws, T, &t);
+    // count and fill are adjacent (count block is 256-aligned): one memset covers both
+    GG_CUDA(cudaMemsetAsync(t.count, 0, (size_t)((char*)t.offset - (char*)t.count), s));
+    { ScopedKernelTimer kt(K_PROJECT, s); g_launches += launch_project(*view, *in, g, t, radii, s); }
+    GG_AFTER("project_kernel");
+    { ScopedKernelTimer kt(K_SCAN, s); g_launches += launch_tile_scan(T, t, s); }
+    GG_AFTER("tile_scan_kernel");
+    if (num_rendered_host) GG_CUDA(cudaMemcpyAsync(num_rendered_host, t.misc, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    return 0;
+}
+
+int gg_forward_color(const gg_view* view, const gg_inputs* in, void* geom_ws, const int32_t* radii, int device,
+                     void* stream) {
+    if (int rc = check_view(view)) return rc;
+    if (int rc = check_inputs(view, in)) return rc;
+    if (view->num_gaussians == 0) return 0;
+    if (!geom_ws || !radii) return fail(GG_E_BADARG, "workspace / radii is NULL");
+    GG_CUDA(cudaSetDevice(device));
+    cudaStream_t s = (cudaStream_t)stream;
+    GeomWS g;
+    geom_layout(geom_ws, view->num_gaussians, &g);
+    { ScopedKernelTimer kt(K_SHCOLOR, s); g_launches += launch_sh_color(*view, *in, g, radii, s); }
+    GG_AFTER("sh_color_kernel");
+    return 0;
+}
+
+int gg_forward_render(const gg_view* view, const gg_inputs* in, const void* geom_ws, void* tile_ws, void* key_ws,
+                      void* record_ws, int64_t instance_capacity, void* image_ws, const int32_t* radii,
+                      float* out_color, float* out_depth, float* out_alpha, int device, void* stream) {
+    if (int rc = check_view(view)) return rc;
+    if (int rc = check_inputs(view, in)) return rc;
+    if (!geom_ws || !tile_ws || !key_ws || !record_ws || !image_ws || !out_color || !out_depth || !out_alpha)
+        return fail(GG_E_BADARG, "NULL workspace or output");
+    if (instance_capacity < 0 || instance_capacity > 0xfffffff0ll) return fail(GG_E_BADARG, "instance_capacity out of range");
+    GG_CUDA(cudaSetDevice(device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const int gx = (view->image_width + TILE - 1) / TILE, gy = (view->image_height + TILE - 1) / TILE;
+    const int T = gx * gy;
+    const size_t P = (size_t)view->image_width * view->image_height;
+    if (view->num_gaussians == 0) {   // upstream: all-zero outputs when there is nothing to draw
+        GG_CUDA(cudaMemsetAsync(out_color, 0, 3 * P * sizeof(float), s));
+        GG_CUDA(cudaMemsetAsync(out_depth, 0, P * sizeof(float), s));
+        GG_CUDA(cudaMemsetAsync(out_alpha, 0, P * sizeof(float), s));
+        return 0;
+    }
+    GeomWS g;
+    TileWS t;
+    RecordWS r;
+    ImageWS img;
+    geom_layout(const_cast<void*>(geom_ws), view->num_gaussians, &g);
+    tile_layout(tile_ws, T, &t);
+    record_layout(record_ws, instance_capacity, &r);
+    image_layout(image_ws, (int64_t)P, &img);
+    const uint32_t cap = (uint32_t)instance_capacity;
+    { ScopedKernelTimer kt(K_EMIT, s); g_launches += launch_emit(*view, g, t, radii, (uint64_t*)key_ws, cap, s); }
+    GG_AFTER("emit_kernel");
+    { ScopedKernelTimer kt(K_SORTPACK, s); g_launches += launch_sort_pack(*view, g, t, (uint64_t*)key_ws, r, cap, s); }
+    GG_AFTER("sort_pack_kernel");
+    { ScopedKernelTimer kt(K_BLENDFWD, s); g_launches += launch_blend_fwd(*view, *in, t, r, img, cap, out_color, out_depth, out_alpha, s); }
+    GG_AFTER("blend_fwd_kernel");
+    return 0;
+}
+
+int gg_backward(const gg_view* view, const gg_inputs* in, const void* tile_ws, const void* record_ws,
+                int64_t instance_capacity, const void* image_ws, const int32_t* radii, void* accum_ws,
+                const float* dL_dcolor, const float* dL_ddepth, const float* dL_dalpha, float* dL_dmeans3D,
+                float* dL_dmeans2D, float* dL_dshs, float* dL_dcolors_precomp, float* dL_dopacities,
+                float* dL_dscales, float* dL_drotations, float* dL_dcov3D, int device, void* stream) {
+    if (int rc = check_view(view)) return rc;
+    if (int rc = check_inputs(view, in)) return rc;
+    if (view->num_gaussians == 0) return 0;
+    if (!tile_ws || !record_ws || !image_ws || !radii || !accum_ws) return fail(GG_E_BADARG, "NULL workspace");
+    if (instance_capacity < 0 || instance_capacity > 0xfffffff0ll) return fail(GG_E_BADARG, "instance_capacity out of range");
+    if (dL_drotations && !aligned16(dL_drotations)) return fail(GG_E_ALIGN, "dL_drotations not 16-byte aligned");
+    if (dL_dshs && view->sh_coeffs == 16 && !aligned16(dL_dshs)) return fail(GG_E_ALIGN, "dL_dshs not 16-byte aligned");
+    GG_CUDA(cudaSetDevice(device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const int gx = (view->image_width + TILE - 1) / TILE, gy = (view->image_height + TILE - 1) / TILE;
+    const int T = gx * gy;
+    TileWS t;
+    RecordWS r;
+    ImageWS img;
+    AccumWS acc;
+    tile_layout(const_cast<void*>(tile_ws), T, &t);
+    record_layout(const_cast<void*>(record_ws), instance_capacity, &r);
+    image_layout(const_cast<void*>(image_ws), (int64_t)view->image_width * view->image_height, &img);
+    accum_layout(accum_ws, view->num_gaussians, &acc);
+    { ScopedKernelTimer kt(K_BLENDBWD, s); g_launches += launch_blend_bwd(*view, *in, t, r, img, dL_dcolor, dL_ddepth, dL_dalpha, acc, s); }
+    GG_AFTER("blend_bwd_kernel");
+    {
+        ScopedKernelTimer kt(K_PREBWD, s);
+        g_launches += launch_preprocess_bwd(*view, *in, radii, acc, dL_dmeans3D, dL_dmeans2D, dL_dshs,
+                                            dL_dcolors_precomp, dL_dopacities, dL_dscales, dL_drotations, dL_dcov3D, s);
+    }
+    GG_AFTER("preprocess_bwd_kernel");
+    return 0;
+}
+
+int gg_mark_visible(int32_t num_gaussians, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                    uint8_t* visible, int device, void* stream) {
+    (void)projmatrix;
+    if (num_gaussians < 0) return fail(GG_E_BADARG, "negative num_gaussians");
+    if (num_gaussians == 0) return 0;
+    if (!means3D || !viewmatrix || !visible) return fail(GG_E_BADARG, "NULL argument");
+    GG_CUDA(cudaSetDevice(device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const gg_view* view = nullptr;
+    g_launches += launch_mark_visible(num_gaussians, means3D, viewmatrix, visible, s);
+    GG_AFTER("mark_visible_kernel");
+    return 0;
+}
+
+int gg_debug_read_geom(const gg_view* view, const void* geom_ws, float* xy, float* depth, float* conic_opacity,
+                       float* rgb, uint32_t* rect, int device, void* stream) {
+    if (int rc = check_view(view)) return rc;
+    if (!geom_ws) return fail(GG_E_BADARG, "geom_ws is NULL");
+    const int64_t N = view->num_gaussians;
+    if (N == 0) return 0;
+    GG_CUDA(cudaSetDevice(device));
+    cudaStream_t s = (cudaStream_t)stream;
+    GeomWS g;
+    geom_layout(const_cast<void*>(geom_ws), N, &g);
+    const cudaMemcpyKind k = cudaMemcpyDefault;
+    if (xy) GG_CUDA(cudaMemcpyAsync(xy, g.xy, N * 8, k, s));
+    if (depth) GG_CUDA(cudaMemcpyAsync(depth, g.depth, N * 4, k, s));
+    if (conic_opacity) GG_CUDA(cudaMemcpyAsync(conic_opacity, g.conic_o, N * 16, k, s));
+    if (rgb) GG_CUDA(cudaMemcpyAsync(rgb, g.rgb, N * 12, k, s));
+    if (rect) {   // unpack on the host side is not possible for device destinations: copy packed pairs
+        GG_CUDA(cudaMemcpyAsync(rect, g.rect, N * 8, k, s));
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,259 @@
+// project.cu -- forward stage 1:
+//   project_kernel   per-Gaussian cull, EWA 3D->2D covariance, conic, radius, tile rectangle, and
+//                    per-tile instance counts (replaces upstream preprocessCUDA + tiles_touched)
+//   tile_scan_kernel exclusive scan of the per-tile counts -> tile ranges + K
+//                    (replaces InclusiveSum over Gaussians AND identifyTileRanges: ranges come
+//                    straight out of the scan because instances are bucketed by tile)
+//   sh_color_kernel  SH(deg<=3) -> RGB (+0.5, clamp), staged through padded shared memory with
+//                    16-byte async copies so the 192 B/Gaussian read is fully coalesced
+//   mark_visible_kernel
+#include "common.cuh"
+
+namespace gg {
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+project_kernel(int N, const float* __restrict__ means3D, const float* __restrict__ scales,
+               const float* __restrict__ rotations, const float* __restrict__ cov3D_precomp,
+               const float* __restrict__ opacities, const float* __restrict__ viewmatrix,
+               const float* __restrict__ projmatrix, int W, int H, int gx, int gy, float tanfovx, float tanfovy,
+               float mod, GeomWS g, uint32_t* __restrict__ tile_count, int32_t* __restrict__ radii) {
+    __shared__ float cam[32];
+    if (threadIdx.x < 16) cam[threadIdx.x] = viewmatrix[threadIdx.x];
+    else if (threadIdx.x < 32) cam[threadIdx.x] = projmatrix[threadIdx.x - 16];
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const float* V = cam;
+    const float* Pm = cam + 16;
+    const float x = means3D[3 * (size_t)i], y = means3D[3 * (size_t)i + 1], z = means3D[3 * (size_t)i + 2];
+
+    int rad_out = 0;
+    uint2 rect = make_uint2(0u, 0u);
+    float2 xy = make_float2(0.f, 0.f);
+    float4 con = make_float4(0.f, 0.f, 0.f, 0.f);
+    float depth = 0.f;
+    int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+
+    float c6[6];
+    if (cov3D_precomp) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) c6[k] = cov3D_precomp[6 * (size_t)i + k];
+    } else {
+        const float s[3] = {scales[3 * (size_t)i], scales[3 * (size_t)i + 1], scales[3 * (size_t)i + 2]};
+        const float4 q4 = reinterpret_cast<const float4*>(rotations)[i];
+        const float q[4] = {q4.x, q4.y, q4.z, q4.w};
+        cov3d_from_scale_rot(s, mod, q, c6);
+    }
+    const float focal_x = W / (2.0f * tanfovx), focal_y = H / (2.0f * tanfovy);
+    Ewa e;
+    ewa_project(V, x, y, z, c6, focal_x, focal_y, tanfovx, tanfovy, e);
+    if (e.tvz > NEAR_Z && e.det != 0.0f) {
+        const float hx = Pm[0] * x + Pm[4] * y + Pm[8] * z + Pm[12];
+        const float hy = Pm[1] * x + Pm[5] * y + Pm[9] * z + Pm[13];
+        const float hw = Pm[3] * x + Pm[7] * y + Pm[11] * z + Pm[15];
+        const float pw = 1.0f / (hw + 0.0000001f);
+        const float det_inv = 1.f / e.det;
+        const float mid = 0.5f * (e.a + e.c);
+        const float lam = mid + sqrtf(fmaxf(0.1f, mid * mid - e.det));
+        const float rad = ceilf(3.f * sqrtf(lam));
+        const float px = ((hx * pw + 1.0f) * W - 1.0f) * 0.5f;
+        const float py = ((hy * pw + 1.0f) * H - 1.0f) * 0.5f;
+        if (isfinite(rad) && isfinite(px) && isfinite(py)) {
+            // (int)(v/16) with clamp to [0, grid]: clamp-then-truncate == truncate-then-clamp
+            x0 = (int)fminf(fmaxf((px - rad) / (float)TILE, 0.f), (float)gx);
+            y0 = (int)fminf(fmaxf((py - rad) / (float)TILE, 0.f), (float)gy);
+            x1 = (int)fminf(fmaxf((px + rad + (float)(TILE - 1)) / (float)TILE, 0.f), (float)gx);
+            y1 = (int)fminf(fmaxf((py + rad + (float)(TILE - 1)) / (float)TILE, 0.f), (float)gy);
+            if ((x1 - x0) * (y1 - y0) > 0) {
+                rad_out = (int)rad;
+                rect = make_uint2((uint32_t)x0 | ((uint32_t)y0 << 16), (uint32_t)x1 | ((uint32_t)y1 << 16));
+                xy = make_float2(px, py);
+                con = make_float4(e.c * det_inv, -e.b * det_inv, e.a * det_inv, opacities[i]);
+                depth = e.tvz;
+            }
+        }
+    }
+    radii[i] = rad_out;
+    g.xy[i] = xy;
+    g.depth[i] = depth;
+    g.conic_o[i] = con;
+    g.rect[i] = rect;
+    if (rad_out > 0) {
+        for (int ty = y0; ty < y1; ty++)
+            for (int tx = x0; tx < x1; tx++) atomicAdd(&tile_count[ty * gx + tx], 1u);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// One CTA scans all T tile counts (T <= a few 10^4): thread-serial chunks + warp-shuffle scan.
+__global__ void __launch_bounds__(1024) tile_scan_kernel(int T, const uint32_t* __restrict__ count,
+                                                         uint32_t* __restrict__ offset, uint32_t* __restrict__ misc) {
+    __shared__ uint32_t warp_tot[32];
+    const int tid = threadIdx.x;
+    const int per = (T + 1023) / 1024;
+    const int beg = min(tid * per, T), end = min(beg + per, T);
+    uint32_t local = 0;
+    for (int i = beg; i < end; i++) local += count[i];
+    // inclusive warp scan
+    uint32_t v = local;
+    const int lane = tid & 31, wid = tid >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t n = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += n;
+    }
+    if (lane == 31) warp_tot[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t w = warp_tot[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t n = __shfl_up_sync(0xffffffffu, w, d);
+            if (lane >= d) w += n;
+        }
+        warp_tot[lane] = w;
+    }
+    __syncthreads();
+    uint32_t run = v - local + (wid > 0 ? warp_tot[wid - 1] : 0u);   // exclusive prefix of this chunk
+    for (int i = beg; i < end; i++) {
+        offset[i] = run;
+        run += count[i];
+    }
+    if (tid == 1023) {
+        offset[T] = warp_tot[31];
+        misc[0] = warp_tot[31];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// SH -> RGB.  M == 16 fast path: a CTA of 128 threads stages its 128 x 192 B contiguous slab with
+// coalesced 16-byte cp.async into rows padded to 13 x 16 B (LDS.128 conflict-free), then every
+// thread evaluates its own Gaussian from registers.
+constexpr int SH_BLOCK = 128;
+constexpr int SH_ROW_U = 13;  // padded row stride in 16-byte units (12 used)
+
+__device__ __forceinline__ void sh_to_rgb(int deg, const float* sh /*[M*3]*/, float dx, float dy, float dz, float* rgb) {
+    float b[16];
+    sh_basis(deg, dx, dy, dz, b);
+    const int nb = (deg + 1) * (deg + 1);
+    float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        if (k < nb) {
+            r0 += b[k] * sh[3 * k];
+            r1 += b[k] * sh[3 * k + 1];
+            r2 += b[k] * sh[3 * k + 2];
+        }
+    }
+    rgb[0] = fmaxf(r0 + 0.5f, 0.f);
+    rgb[1] = fmaxf(r1 + 0.5f, 0.f);
+    rgb[2] = fmaxf(r2 + 0.5f, 0.f);
+}
+
+__global__ void __launch_bounds__(SH_BLOCK)
+sh_color16_kernel(int N, int deg, const float* __restrict__ means3D, const float* __restrict__ shs,
+                  const float* __restrict__ campos, const int32_t* __restrict__ radii, float* __restrict__ rgb_out) {
+    __shared__ __align__(16) float4 rows[SH_BLOCK * SH_ROW_U];
+    const int base = blockIdx.x * SH_BLOCK;
+    const int i = base + threadIdx.x;
+    const int nG = min(SH_BLOCK, N - base);
+    const bool live = (i < N) && (radii[i] > 0);
+    if (!__syncthreads_or(live)) return;   // whole slab culled: skip its 24 KB read
+    const float4* src = reinterpret_cast<const float4*>(shs) + (size_t)base * 12;
+    for (int u = threadIdx.x; u < nG * 12; u += SH_BLOCK) {
+        const int gI = u / 12, j = u - gI * 12;
+        cp_async16(&rows[gI * SH_ROW_U + j], src + u);
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    if (!live) return;
+    float sh[48];
+#pragma unroll
+    for (int j = 0; j < 12; j++) {
+        const float4 q = rows[threadIdx.x * SH_ROW_U + j];
+        sh[4 * j] = q.x; sh[4 * j + 1] = q.y; sh[4 * j + 2] = q.z; sh[4 * j + 3] = q.w;
+    }
+    float dx = means3D[3 * (size_t)i] - campos[0], dy = means3D[3 * (size_t)i + 1] - campos[1],
+          dz = means3D[3 * (size_t)i + 2] - campos[2];
+    const float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
+    float rgb[3];
+    sh_to_rgb(deg, sh, dx * inv, dy * inv, dz * inv, rgb);
+    rgb_out[3 * (size_t)i] = rgb[0];
+    rgb_out[3 * (size_t)i + 1] = rgb[1];
+    rgb_out[3 * (size_t)i + 2] = rgb[2];
+}
+
+// generic M (1, 4, 9, ...) or precomputed colours: direct loads
+__global__ void __launch_bounds__(256)
+sh_color_generic_kernel(int N, int M, int deg, const float* __restrict__ means3D, const float* __restrict__ shs,
+                        const float* __restrict__ colors_precomp, const float* __restrict__ campos,
+                        const int32_t* __restrict__ radii, float* __restrict__ rgb_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N || radii[i] <= 0) return;
+    float rgb[3];
+    if (colors_precomp) {
+        rgb[0] = colors_precomp[3 * (size_t)i]; rgb[1] = colors_precomp[3 * (size_t)i + 1]; rgb[2] = colors_precomp[3 * (size_t)i + 2];
+    } else {
+        float sh[48];
+        const int nb = (deg + 1) * (deg + 1);
+#pragma unroll
+        for (int k = 0; k < 48; k++) sh[k] = (k < 3 * nb) ? shs[(size_t)i * M * 3 + k] : 0.f;
+        float dx = means3D[3 * (size_t)i] - campos[0], dy = means3D[3 * (size_t)i + 1] - campos[1],
+              dz = means3D[3 * (size_t)i + 2] - campos[2];
+        const float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
+        sh_to_rgb(deg, sh, dx * inv, dy * inv, dz * inv, rgb);
+    }
+    rgb_out[3 * (size_t)i] = rgb[0];
+    rgb_out[3 * (size_t)i + 1] = rgb[1];
+    rgb_out[3 * (size_t)i + 2] = rgb[2];
+}
+
+__global__ void __launch_bounds__(256)
+mark_visible_kernel(int N, const float* __restrict__ means3D, const float* __restrict__ viewmatrix,
+                    uint8_t* __restrict__ visible) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const float x = means3D[3 * (size_t)i], y = means3D[3 * (size_t)i + 1], z = means3D[3 * (size_t)i + 2];
+    const float tz = viewmatrix[2] * x + viewmatrix[6] * y + viewmatrix[10] * z + viewmatrix[14];
+    visible[i] = tz > NEAR_Z ? 1 : 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+int launch_project(const gg_view& v, const gg_inputs& in, const GeomWS& g, const TileWS& t, int32_t* radii,
+                   cudaStream_t s) {
+    const int N = v.num_gaussians;
+    if (N == 0) return 0;
+    const int gx = (v.image_width + TILE - 1) / TILE, gy = (v.image_height + TILE - 1) / TILE;
+    project_kernel<<<(N + 255) / 256, 256, 0, s>>>(N, in.means3D, in.scales, in.rotations, in.cov3D_precomp,
+                                                   in.opacities, in.viewmatrix, in.projmatrix, v.image_width,
+                                                   v.image_height, gx, gy, v.tanfovx, v.tanfovy, v.scale_modifier, g,
+                                                   t.count, radii);
+    return 1;
+}
+
+int launch_tile_scan(int T, const TileWS& t, cudaStream_t s) {
+    tile_scan_kernel<<<1, 1024, 0, s>>>(T, t.count, t.offset, t.misc);
+    return 1;
+}
+
+int launch_sh_color(const gg_view& v, const gg_inputs& in, const GeomWS& g, const int32_t* radii, cudaStream_t s) {
+    const int N = v.num_gaussians;
+    if (N == 0) return 0;
+    if (!in.colors_precomp && v.sh_coeffs == 16) {
+        sh_color16_kernel<<<(N + SH_BLOCK - 1) / SH_BLOCK, SH_BLOCK, 0, s>>>(N, v.sh_degree, in.means3D, in.shs,
+                                                                             in.campos, radii, g.rgb);
+    } else {
+        sh_color_generic_kernel<<<(N + 255) / 256, 256, 0, s>>>(N, v.sh_coeffs, v.sh_degree, in.means3D, in.shs,
+                                                                in.colors_precomp, in.campos, radii, g.rgb);
+    }
+    return 1;
+}
+
+int launch_mark_visible(int N, const float* means3D, const float* viewmatrix, uint8_t* visible, cudaStream_t s) {
+    if (N == 0) return 0;
+    mark_visible_kernel<<<(N + 255) / 256, 256, 0, s>>>(N, means3D, viewmatrix, visible);
+    return 1;
+}
+
+}  // namespace gg

@@ -1,0 +1,154 @@
+/* gg_raster.h -- C ABI of the B200-native differentiable Gaussian-splat rasterizer.
+ *
+ * This is the drop-in boundary for the hot path of eth-ait/Gaussian-Garments.  In the
+ * reference that boundary is the pybind11 module `_C` of the third-party package
+ * `diff_gaussian_rasterization_depth_alpha` (imported at
+ * /root/reference/gaussian_renderer/__init__.py:16, installed by /root/reference/setup.sh:26-29),
+ * which the Python classes `GaussianRasterizationSettings` / `GaussianRasterizer` bind to
+ * (/root/reference/gaussian_renderer/__init__.py:39-54 and :103-111).  Each entry point below
+ * names the `_C` function (upstream recall) or reference call site it replaces.
+ *
+ * Conventions
+ *   - plain C: device pointers are `void*`/typed pointers to CUDA device memory, sizes are
+ *     integers, the stream is a `cudaStream_t` passed as `void*`.  No torch types.
+ *   - the library never allocates or frees device memory: every output and workspace is
+ *     caller-allocated (the Python host lets torch's caching allocator own them; SURVEY.md 8b
+ *     "Ownership").  Workspace sizes come from the gg_*_workspace_bytes() queries.
+ *   - every function returns 0 on success, a positive cudaError_t value or a negative GG_E_*
+ *     code on failure; gg_last_error() returns a thread-local description.  Nothing throws or
+ *     exits across the boundary.
+ *   - re-entrant, no global mutable state; `device` is re-asserted with cudaSetDevice because
+ *     autograd calls backward on a worker thread (SURVEY.md 8b "Threading / streams").
+ *   - all floating tensors are fp32, contiguous, 16-byte aligned base pointers.
+ */
+#ifndef GG_RASTER_H_
+#define GG_RASTER_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GG_ABI_VERSION 1
+#define GG_TILE 16
+
+#define GG_E_BADARG (-1)   /* null pointer / inconsistent sizes */
+#define GG_E_ALIGN (-2)    /* pointer not 16-byte aligned */
+#define GG_E_OVERFLOW (-3) /* num_rendered exceeds the instance workspace capacity given */
+
+/* The scalar part of GaussianRasterizationSettings (gaussian_renderer/__init__.py:39-52).
+ * The tensor-valued settings (bg, viewmatrix, projmatrix, campos) stay on the device and are
+ * passed by pointer, exactly as the reference passes CUDA tensors. */
+typedef struct gg_view {
+    int32_t num_gaussians; /* N  = means3D.shape[0]                                   */
+    int32_t sh_coeffs;     /* M  = shs.shape[1]; 0 when colors_precomp is used        */
+    int32_t sh_degree;     /* D  = raster_settings.sh_degree (active degree, 0..3)    */
+    int32_t image_width;   /* raster_settings.image_width                             */
+    int32_t image_height;  /* raster_settings.image_height                            */
+    float tanfovx;         /* raster_settings.tanfovx                                 */
+    float tanfovy;         /* raster_settings.tanfovy                                 */
+    float scale_modifier;  /* raster_settings.scale_modifier                          */
+    int32_t prefiltered;   /* raster_settings.prefiltered (accepted, unused as upstream) */
+    int32_t debug;         /* raster_settings.debug: sync + check after every launch  */
+} gg_view;
+
+/* Device-resident inputs of one rasterizer call (the 8 call kwargs of
+ * gaussian_renderer/__init__.py:103-111 plus the 4 tensor settings). Unused alternatives NULL. */
+typedef struct gg_inputs {
+    const float* means3D;        /* [N,3]                                            */
+    const float* shs;            /* [N,M,3] or NULL                                  */
+    const float* colors_precomp; /* [N,3]   or NULL                                  */
+    const float* opacities;      /* [N,1]                                            */
+    const float* scales;         /* [N,3]   or NULL                                  */
+    const float* rotations;      /* [N,4] wxyz or NULL                               */
+    const float* cov3D_precomp;  /* [N,6]   or NULL                                  */
+    const float* bg;             /* [3]                                              */
+    const float* viewmatrix;     /* [4,4] world_view_transform (scene/cameras.py:59) */
+    const float* projmatrix;     /* [4,4] full_proj_transform  (scene/cameras.py:61) */
+    const float* campos;         /* [3]   camera_center        (scene/cameras.py:62) */
+} gg_inputs;
+
+/* ---- workspace size queries (bytes) ------------------------------------------------------ */
+/* geom: per-Gaussian projected records, transient within forward.
+ * tile: per-tile counters / offsets; offsets are needed again by backward.
+ * image: per-pixel n_contrib + final transmittance, needed again by backward.           */
+int gg_forward_workspace_bytes(const gg_view* view, size_t* geom_bytes, size_t* tile_bytes,
+                               size_t* image_bytes);
+/* keys: transient (tile-bucketed depth keys); records: packed sorted per-instance records,
+ * needed again by backward.  `num_rendered` = K.                                          */
+int gg_instance_workspace_bytes(int64_t num_rendered, size_t* key_bytes, size_t* record_bytes);
+/* per-Gaussian gradient accumulators, transient within backward (must be zero-filled).  */
+int gg_backward_workspace_bytes(const gg_view* view, size_t* accum_bytes);
+
+/* ---- forward, stage 1a: replaces the first half of `_C.rasterize_gaussians`
+ * (geometry part of preprocessCUDA + InclusiveSum + the num_rendered read-back).
+ * Launches: project (3D->2D covariance, cull, tile rectangle, per-tile counts) and the tile
+ * scan.  Writes radii[N] (int32, an output tensor of the call).  `num_rendered_host` may be
+ * NULL or a pinned host word that receives K through an async copy enqueued on `stream`
+ * right after the scan: record an event after this call and wait on it before reading.    */
+int gg_forward_project(const gg_view* view, const gg_inputs* in, void* geom_ws, void* tile_ws,
+                       int32_t* radii, uint32_t* num_rendered_host, int device, void* stream);
+
+/* ---- forward, stage 1b: the colour part of preprocessCUDA (SH deg<=3 -> RGB, +0.5, clamp;
+ * or a copy of colors_precomp).  Enqueued behind the K read-back so that the host's wait
+ * for K overlaps this kernel (the 57.6 MB SH read at 300k Gaussians).                     */
+int gg_forward_color(const gg_view* view, const gg_inputs* in, void* geom_ws, const int32_t* radii,
+                     int device, void* stream);
+
+/* ---- forward, stage 2: replaces the second half of `_C.rasterize_gaussians`
+ * (duplicateWithKeys + RadixSort + identifyTileRanges + renderCUDA).
+ * Launches: instance emit, per-tile depth sort + record packing, front-to-back blend.
+ * `instance_capacity` is the K the key/record workspaces were sized for.
+ * Outputs: out_color[3,H,W], out_depth[1,H,W], out_alpha[1,H,W].                          */
+int gg_forward_render(const gg_view* view, const gg_inputs* in, const void* geom_ws, void* tile_ws,
+                      void* key_ws, void* record_ws, int64_t instance_capacity, void* image_ws,
+                      const int32_t* radii, float* out_color, float* out_depth, float* out_alpha,
+                      int device, void* stream);
+
+/* ---- backward: replaces `_C.rasterize_gaussians_backward`
+ * (renderCUDA bwd + computeCov2DCUDA + preprocessCUDA bwd).
+ * Upstream gradients dL_dcolor[3,H,W], dL_ddepth[1,H,W], dL_dalpha[1,H,W] (any may be NULL =
+ * zeros).  Output gradients (any may be NULL = not wanted): dL_dmeans3D[N,3],
+ * dL_dmeans2D[N,3] (side channel, z = 0; consumer scene/gaussian_model.py:410-412),
+ * dL_dshs[N,M,3], dL_dcolors_precomp[N,3], dL_dopacities[N,1], dL_dscales[N,3],
+ * dL_drotations[N,4], dL_dcov3D[N,6].  accum_ws must be zero-filled on entry;
+ * `instance_capacity` must be the value given to gg_forward_render for `record_ws`.      */
+int gg_backward(const gg_view* view, const gg_inputs* in, const void* tile_ws, const void* record_ws,
+                int64_t instance_capacity, const void* image_ws, const int32_t* radii, void* accum_ws,
+                const float* dL_dcolor,
+                const float* dL_ddepth, const float* dL_dalpha, float* dL_dmeans3D, float* dL_dmeans2D,
+                float* dL_dshs, float* dL_dcolors_precomp, float* dL_dopacities, float* dL_dscales,
+                float* dL_drotations, float* dL_dcov3D, int device, void* stream);
+
+/* ---- replaces `_C.mark_visible` (GaussianRasterizer.markVisible; not called by the
+ * reference, kept for API completeness): visible[i] = (view-space z > 0.2).               */
+int gg_mark_visible(int32_t num_gaussians, const float* means3D, const float* viewmatrix,
+                    const float* projmatrix, uint8_t* visible, int device, void* stream);
+
+/* ---- introspection ------------------------------------------------------------------------ */
+/* copies stage-1 per-Gaussian records out of geom_ws for stage-wise parity tests
+ * (xy[N,2], depth[N], conic_opacity[N,4], rgb[N,3], rect[N,2] uint32 packed as
+ * x0 | y0<<16, x1 | y1<<16); any may be NULL.                                             */
+int gg_debug_read_geom(const gg_view* view, const void* geom_ws, float* xy, float* depth,
+                       float* conic_opacity, float* rgb, uint32_t* rect, int device, void* stream);
+/* number of kernels this library launched (process-wide: backward runs on an autograd worker
+ * thread) since the last reset.                                                            */
+int64_t gg_launch_count(int reset);
+/* Optional per-kernel timing (off by default): when enabled every kernel launch is bracketed
+ * by CUDA events on the launching stream; gg_kernel_times() waits for the most recent launch
+ * of each kernel and writes its duration in ms into ms_out[gg_kernel_count()] (-1 = not
+ * launched since enabling).  Meant for bench.py's roofline block, not for the timed region. */
+int gg_kernel_timing(int enable);
+int gg_kernel_count(void);
+const char* gg_kernel_name(int slot);
+int gg_kernel_times(float* ms_out);
+const char* gg_last_error(void);
+const char* gg_version(void);
+int gg_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GG_RASTER_H_ */
