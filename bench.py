@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""bench.py -- views/s, forward+backward, 300k mesh-bound Gaussians @1080p (BASELINE.json configs[1]).
+
+    python bench.py --gpus 1 --steps 100 --warmup 20
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference --steps 5 --warmup 1      # CPU oracle arm (no CUDA rasterizer)
+
+A "step" is one pass of the hot path over one view per GPU: GaussianRasterizer forward, L1 loss
+against a fixed random ground-truth image, backward into means3D/scales/rotations/opacities/SH,
+and -- for N > 1 -- one NCCL all-reduce of the flat gradient bucket (views are sharded one per
+GPU; weak scaling).  Rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "views/sec fwd+bwd @300k Gaussians 1080p"
+UNIT = "views/s"
+WORKLOAD = "cfg2: 300k mesh-bound Gaussians (synthetic cylinder template, 50k faces x6), 1920x1080, SH degree 3"
+N_GAUSS, WIDTH, HEIGHT, N_CAMS = 300_000, 1920, 1080, 8
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--gaussians", type=int, default=N_GAUSS)
+    ap.add_argument("--width", type=int, default=WIDTH)
+    ap.add_argument("--height", type=int, default=HEIGHT)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-views", type=int, default=3, help="views timed for the cpu_baseline block")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons through NVML while the timed region runs."""
+
+    REASONS = {0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x10: "sync_boost",
+               0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown",
+               0x100: "display_clock_setting"}
+
+    def __init__(self, index: int, period=0.05):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(int(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+                try:
+                    mask = int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    mask = int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------
+def algorithmic_bytes(N, K, P, T, M=16):
+    """SURVEY.md 8d / DESIGN.md: compulsory bytes per launch of each kernel (this repo's kernel split)."""
+    return {
+        "project": (44 + 4) * N + 44 * N + 4 * K,              # inputs + geom records written + tile-count atomics
+        "tile_scan": 8 * T,
+        "sh_color": (12 + 12 * M) * N + 12 * N,
+        "emit": 20 * N + 8 * K,
+        "sort_pack": 8 * K + 36 * K + 48 * K,                   # keys in, gathered geom, packed planes out
+        "blend_fwd": 48 * K + 28 * P,
+        "blend_bwd": 48 * K + 28 * P + 40 * N,
+        "preprocess_bwd": (40 + 44 + 12 * M) * N + (56 + 12 * M) * N,
+    }
+
+
+def make_scene(args, dev):
+    import diff_gaussian_rasterization_depth_alpha  # noqa: F401 (registers gaussian_garments_b200)
+    import gaussian_garments_b200 as gg
+    st = gg.scenes.mesh_bound_state(args.gaussians)
+    cams = gg.scenes.ring_cameras(N_CAMS, width=args.width, height=args.height)
+    g = torch.Generator().manual_seed(gg.scenes.SEED + 1)
+    gts = [torch.rand(3, args.height, args.width, generator=g) for _ in range(2)]
+    return gg, st, cams, gts
+
+
+def run_reference(args, rank, world):
+    """CPU arm: the oracle port of the path (the reference's own rasterizer is a CUDA-only,
+    un-vendored extension -- there is no reference CPU implementation to run)."""
+    if rank != 0:
+        return
+    from oracle import c_oracle
+    import diff_gaussian_rasterization_depth_alpha  # noqa: F401
+    import gaussian_garments_b200 as gg
+    st = gg.scenes.mesh_bound_state(args.gaussians)
+    cams = gg.scenes.ring_cameras(N_CAMS, width=args.width, height=args.height)
+    g = torch.Generator().manual_seed(gg.scenes.SEED + 1)
+    gt = torch.rand(3, args.height, args.width, generator=g)
+    cores = c_oracle.num_threads()
+
+    def one(cam):
+        S = (cam.image_height, cam.image_width, cam.tanfovx, cam.tanfovy, st.bg, 1.0, cam.world_view_transform,
+             cam.full_proj_transform, st.sh_degree, cam.camera_center, False, False)
+        color, radii, depth, alpha, ctx, _ = c_oracle.rasterize_forward(S, st.means3D, st.shs, None, st.opacities,
+                                                                         st.scales, st.rotations, None)
+        gC = torch.sign(color - gt) / color.numel()
+        ctx.backward(gC, None, None)
+        ctx.close()
+
+    for i in range(args.warmup):
+        one(cams[i % N_CAMS])
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        one(cams[i % N_CAMS])
+    dt = time.perf_counter() - t0
+    v = args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "gaussians": args.gaussians, "width": args.width, "height": args.height},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{args.steps} views fwd+bwd of the same workload, oracle/gg_oracle.c with OpenMP"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "reference rasterizer is CUDA-only and un-vendored; this arm times the CPU oracle port"}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU oracle arm)")
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    gg, st_cpu, cams_cpu, gts_cpu = make_scene(args, dev)
+    from gaussian_garments_b200 import _capi
+    from gaussian_garments_b200.dist import GradBucket
+    dgr = sys.modules["diff_gaussian_rasterization_depth_alpha"]
+    st = st_cpu.to(dev)
+    cams = [c.to(dev) for c in cams_cpu]
+    params = [t.detach().clone().requires_grad_(True) for t in
+              (st.means3D, st.scales, st.rotations, st.opacities, st.shs)]
+    bucket = GradBucket(params, world)
+    gt_dev = [g.to(dev) for g in gts_cpu]
+    flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    H, W = args.height, args.width
+
+    def settings(cam):
+        return dgr.GaussianRasterizationSettings(
+            image_height=H, image_width=W, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, bg=st.bg, scale_modifier=1.0,
+            viewmatrix=cam.world_view_transform, projmatrix=cam.full_proj_transform, sh_degree=st.sh_degree,
+            campos=cam.camera_center, prefiltered=False, debug=False)
+
+    def step(i, gt, cam=None):
+        cam = cam if cam is not None else cams[(i * world + rank) % N_CAMS]
+        means2D = torch.zeros_like(params[0], requires_grad=True)
+        color, radii, depth, alpha = dgr.GaussianRasterizer(raster_settings=settings(cam))(
+            means3D=params[0], means2D=means2D, shs=params[4], colors_precomp=None, opacities=params[3],
+            scales=params[1], rotations=params[2], cov3D_precomp=None)
+        loss = (color - gt).abs().mean()
+        bucket.zero()
+        loss.backward()
+        bucket.all_reduce()
+        return loss
+
+    # ---------------- device-resident timing: `value` ----------------
+    for i in range(args.warmup):
+        step(i, gt_dev[i % 2])
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    sampler = ClockSampler(local)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    _capi.launch_count(reset=True)
+    sampler.start()
+    t_wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush_buf.fill_(i & 0xFF)                      # L2 flush between timed iterations (outside the events)
+        ev[i][0].record()
+        step(i, gt_dev[i % 2])
+        ev[i][1].record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    launches = _capi.launch_count()
+    step_ms = sorted(a.elapsed_time(b) for a, b in ev)
+    total_ms = sum(step_ms)
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = world * args.steps / (total_ms * 1e-3)
+
+    # ---------------- end-to-end through the public API with host buffers: `e2e` ----------------
+    gt_pinned = [g.pin_memory() for g in gts_cpu]
+    cam_pinned = [(c.world_view_transform.pin_memory(), c.full_proj_transform.pin_memory(), c.camera_center.pin_memory())
+                  for c in cams_cpu]
+    gt_stage = torch.empty(3, H, W, device=dev)
+    import copy
+    h2d = gt_pinned[0].numel() * 4 + (16 + 16 + 3) * 4
+
+    def e2e_step(i):
+        ci = (i * world + rank) % N_CAMS
+        gt_stage.copy_(gt_pinned[i % 2], non_blocking=True)
+        cam = copy.copy(cams_cpu[ci])
+        cam.world_view_transform = cam_pinned[ci][0].to(dev, non_blocking=True)
+        cam.full_proj_transform = cam_pinned[ci][1].to(dev, non_blocking=True)
+        cam.camera_center = cam_pinned[ci][2].to(dev, non_blocking=True)
+        loss = step(i, gt_stage, cam)
+        return float(loss.item())                       # D2H read of the step's result
+
+    for i in range(3):
+        e2e_step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e_steps = max(10, args.steps // 2)
+    t0 = time.perf_counter()
+    for i in range(e_steps):
+        e2e_step(i)
+    torch.cuda.synchronize()
+    e_dt = time.perf_counter() - t0
+    t = torch.tensor([e_dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * e_steps / float(t.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- per-kernel roofline (rank 0, outside the timed region) ----------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
+    _capi.kernel_timing(True)
+    acc, Ks = {}, []
+    reps = 8
+    for i in range(reps):
+        flush_buf.fill_(1)
+        step(i, gt_dev[i % 2])
+        torch.cuda.synchronize()
+        for k, v in _capi.kernel_times().items():
+            acc[k] = acc.get(k, 0.0) + v / reps
+        Ks.append(_capi_last_K())
+    _capi.kernel_timing(False)
+    K = int(sum(Ks) / len(Ks))
+    gx, gy = (W + 15) // 16, (H + 15) // 16
+    ab = algorithmic_bytes(args.gaussians, K, W * H, gx * gy)
+    kernels = []
+    for name, ms in sorted(acc.items(), key=lambda kv: -kv[1]):
+        gbs = ab[name] / (ms * 1e-3) / 1e9
+        kernels.append({"kernel": name, "ms": round(ms, 4), "alg_bytes": int(ab[name]), "achieved_gbs": round(gbs, 1),
+                        "frac": round(gbs / peak_gbs, 4)})
+    dom = kernels[0]
+    interactions = 256 * K
+    roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_gbs"], "peak": peak_gbs, "unit": "GB/s",
+                "frac": dom["frac"], "traffic": None, "peak_source": peak_src, "avg_launch_ms": dom["ms"],
+                "num_rendered": K, "pixel_gaussian_pairs": interactions,
+                "note": "blend kernels are FP32/SFU/issue bound by construction (256*K pixel-Gaussian pairs); "
+                        "streaming kernels carry the HBM claim -- see `kernels`",
+                "kernels": kernels, "kernel_ms_sum": round(sum(k["ms"] for k in kernels), 4)}
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline:
+        cpu_baseline = run_cpu_baseline(args, st_cpu, cams_cpu, gts_cpu[0])
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "gaussians": args.gaussians, "width": W, "height": H, "sh_degree": 3,
+                       "views_per_step": world, "parallelism": f"view-dp{world}", "cameras": N_CAMS,
+                       "l2": "flushed between timed steps (256 MiB write, outside the per-step CUDA events)",
+                       "timing": "sum of per-step CUDA-event times, max over ranks"},
+            "step_ms": {"p10": step_ms[len(step_ms) // 10], "median": step_ms[len(step_ms) // 2],
+                        "p90": step_ms[(len(step_ms) * 9) // 10]},
+            "wall_s_timed_region_incl_flush": wall,
+            "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "what": "pinned-host GT image + camera matrices copied H2D every step, public GaussianRasterizer "
+                            "API fwd+L1+bwd, loss read back D2H; wall clock, max over ranks", "steps": e_steps},
+            "roofline": roofline}
+    if cpu_baseline is not None:
+        line["cpu_baseline"] = cpu_baseline
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _capi_last_K():
+    from gaussian_garments_b200 import rasterizer
+    return int(getattr(rasterizer, "LAST_NUM_RENDERED", 0))
+
+
+def run_cpu_baseline(args, st, cams, gt):
+    """Oracle port on the box's host cores, bounded sample of the same workload."""
+    from oracle import c_oracle
+    cores = c_oracle.num_threads()
+    n = max(1, args.cpu_views)
+
+    def one(cam):
+        S = (cam.image_height, cam.image_width, cam.tanfovx, cam.tanfovy, st.bg, 1.0, cam.world_view_transform,
+             cam.full_proj_transform, st.sh_degree, cam.camera_center, False, False)
+        color, radii, depth, alpha, ctx, _ = c_oracle.rasterize_forward(S, st.means3D, st.shs, None, st.opacities,
+                                                                         st.scales, st.rotations, None)
+        ctx.backward(torch.sign(color - gt) / color.numel(), None, None)
+        ctx.close()
+
+    one(cams[0])
+    t0 = time.perf_counter()
+    for i in range(n):
+        one(cams[i % len(cams)])
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n} views fwd+bwd of the same workload (oracle/gg_oracle.c, OpenMP, {cores} threads)"}
+
+
+if __name__ == "__main__":
+    main()

@@ -64,30 +64,36 @@ blend_fwd_kernel(const uint32_t* __restrict__ tile_offset, const float4* __restr
     for (; b < nb; b++) {
         const int st = b % FWD_STAGES;
         mbar_wait(&full[st], (uint32_t)(b / FWD_STAGES) & 1u);
-        if (!done) {
+        // Convergent, predicated inner loop.  (A first version used divergent continue/break here;
+        // ncu showed 2.5 active threads per warp: independent thread scheduling let lanes run ahead
+        // into later iterations and never reconverge.  The warp vote below re-converges the warp
+        // every iteration and doubles as the per-warp early-out.)
+        {
             const int cnt = min(FWD_BATCH, (int)n - b * FWD_BATCH);
             for (int j = 0; j < cnt; j++) {
+                if (__all_sync(0xffffffffu, done)) break;
                 const float4 a = s0[st][j];
                 const float4 c = s1[st][j];
                 const float dx = a.x - fx, dy = a.y - fy;
                 const float power = -0.5f * (a.z * dx * dx + c.x * dy * dy) - a.w * dx * dy;
-                if (power > 0.f) continue;
                 const float alpha = fminf(ALPHA_MAX, c.y * __expf(power));
-                if (alpha < ALPHA_MIN) continue;
+                bool ok = !done && power <= 0.f && alpha >= ALPHA_MIN;
                 const float test_T = T * (1.f - alpha);
-                if (test_T < T_STOP) {
+                if (ok && test_T < T_STOP) {
                     done = true;
-                    break;
+                    ok = false;
                 }
-                const float w = alpha * T;
-                const float4 col = s2[st][j];
-                C0 += col.x * w;
-                C1 += col.y * w;
-                C2 += col.z * w;
-                Dp += c.z * w;
-                Ac += w;
-                T = test_T;
-                last = (uint32_t)(b * FWD_BATCH + j + 1);
+                if (ok) {
+                    const float w = alpha * T;
+                    const float4 col = s2[st][j];
+                    C0 += col.x * w;
+                    C1 += col.y * w;
+                    C2 += col.z * w;
+                    Dp += c.z * w;
+                    Ac += w;
+                    T = test_T;
+                    last = (uint32_t)(b * FWD_BATCH + j + 1);
+                }
             }
         }
         const int n_done = __syncthreads_count(done);   // also: everyone has finished reading stage st

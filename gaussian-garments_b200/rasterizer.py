@@ -46,6 +46,21 @@ class GaussianRasterizationSettings(NamedTuple):
 # one pinned word per (thread, device) for the num_rendered read-back
 _tls = threading.local()
 
+# data_ptr of an input tensor -> (flat fp32 buffer, element offset, shape): when present, backward
+# writes that input's gradient straight into the flat buffer (dist.GradBucket, zero-copy all-reduce).
+grad_sinks = {}
+
+LAST_NUM_RENDERED = 0   # K of the most recent forward (bench/diagnostics)
+
+
+def _sink_of(t):
+    if t is None or not torch.is_tensor(t) or t.numel() == 0 or not grad_sinks:
+        return None
+    ent = grad_sinks.get(t.data_ptr())
+    if ent is None or tuple(t.shape) != ent[2] or not t.is_contiguous():
+        return None
+    return ent
+
 
 def _pinned_word(device_index: int) -> torch.Tensor:
     cache = getattr(_tls, "words", None)
@@ -161,8 +176,12 @@ class _RasterizeGaussians(torch.autograd.Function):
                 print("\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
             raise
 
+        global LAST_NUM_RENDERED
+        LAST_NUM_RENDERED = K
         ctx.raster_settings = s
         ctx.num_rendered = K
+        ctx.sinks = tuple(_sink_of(t) for t in (means3D, sh, colors_precomp, opacities, scales, rotations,
+                                                cov3Ds_precomp))
         ctx.shapes = (N, M)
         ctx.has = (shs is not None, col is not None, sc is not None, cv is not None)
         # NOTE: `color` is deliberately NOT saved: the reference's ssim() multiplies it in place before
@@ -203,15 +222,26 @@ class _RasterizeGaussians(torch.autograd.Function):
         view = _view_struct(s, N, M)
         inputs = GGInputs(_ptr(m3), _ptr(shs), _ptr(col), _ptr(op), _ptr(sc), _ptr(ro), _ptr(cv),
                           _ptr(bg), _ptr(vm), _ptr(pm), _ptr(cp))
-        E = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=dev)
-        g_m3 = E(N, 3) if need[0] else None
-        g_m2 = E(N, 3) if need[1] else None
-        g_sh = E(N, M, 3) if (has_sh and need[2]) else None
-        g_col = E(N, 3) if (has_col and need[3]) else None
-        g_op = E(N, 1) if need[4] else None
-        g_sc = E(N, 3) if (has_sr and need[5]) else None
-        g_ro = E(N, 4) if (has_sr and need[6]) else None
-        g_cv = E(N, 6) if (has_cov and need[7]) else None
+        sinks = ctx.sinks
+
+        def E(slot, *shape):
+            ent = sinks[slot] if slot is not None else None
+            if ent is not None and ent[2] == tuple(shape):
+                flat, off, _ = ent
+                n = 1
+                for d in shape:
+                    n *= d
+                return flat[off:off + n].view(*shape)        # fresh view: autograd adopts it as .grad
+            return torch.empty(*shape, dtype=torch.float32, device=dev)
+
+        g_m3 = E(0, N, 3) if need[0] else None
+        g_m2 = E(None, N, 3) if need[1] else None
+        g_sh = E(1, N, M, 3) if (has_sh and need[2]) else None
+        g_col = E(2, N, 3) if (has_col and need[3]) else None
+        g_op = E(3, N, 1) if need[4] else None
+        g_sc = E(4, N, 3) if (has_sr and need[5]) else None
+        g_ro = E(5, N, 4) if (has_sr and need[6]) else None
+        g_cv = E(6, N, 6) if (has_cov and need[7]) else None
         try:
             with torch.cuda.device(dev):
                 sp = torch.cuda.current_stream(dev).cuda_stream

@@ -59,7 +59,7 @@ def run_cuda(settings, st, grads=None, colors_precomp=None, cov3D_precomp=None, 
     return out
 
 
-def run_c_oracle(settings, st, grads=None, colors_precomp=None, cov3D_precomp=None, fragile_eps=1e-3):
+def run_c_oracle(settings, st, grads=None, colors_precomp=None, cov3D_precomp=None, fragile_eps=2e-4):
     S = cpu_settings(settings)
     use_cov = cov3D_precomp is not None
     color, radii, depth, alpha, ctx, frag = c_oracle.rasterize_forward(
@@ -75,7 +75,7 @@ def rel_inf(a, b):
     return float((a.float() - b.float()).abs().max() / b.float().abs().max().clamp_min(1e-12))
 
 
-def assert_images_close(got, ref, tol=RGB_TOL, max_fragile_frac=2e-3):
+def assert_images_close(got, ref, tol=RGB_TOL, max_fragile_frac=1e-2):
     """All pixels within tol except those the oracle flags as sitting on a discrete threshold
     (alpha ~ 1/255 or T ~ 1e-4), which must stay a tiny fraction."""
     frag = ref["fragile"]

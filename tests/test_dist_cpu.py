@@ -1,0 +1,90 @@
+"""CPU tests of the N>1 host logic: world_size-2 gloo run of the flat gradient bucket
+(the rasterizer itself needs a GPU; here each rank's 'backward' is a deterministic stand-in that
+writes into the bucket's sinks the same way gg_backward does)."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import helpers as h
+
+gg = h.gg
+from gaussian_garments_b200.dist import GradBucket, shard_views  # noqa: E402
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _fake_view_grads(params, view):
+    g = torch.Generator().manual_seed(1000 + view)
+    return [torch.randn(p.shape, generator=g) for p in params]
+
+
+def _worker(rank, world, port, n_views, out_dir):
+    sys.path.insert(0, h.ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    params = [torch.zeros(50, 3, requires_grad=True), torch.zeros(50, 16, 3, requires_grad=True),
+              torch.zeros(50, 1, requires_grad=True)]
+    bucket = GradBucket(params, world)
+    steps = n_views // world
+    mine = shard_views(n_views, rank, world)
+    results = []
+    for s in range(steps):
+        bucket.zero()
+        grads = _fake_view_grads(params, mine[s])
+        for i, g in enumerate(grads):          # what backward does: write straight into the sink views,
+            v = bucket.view(i)                 # which autograd's AccumulateGrad then adopts as .grad
+            v.copy_(g)
+            params[i].grad = v
+        bucket.all_reduce()
+        for i, p in enumerate(params):
+            assert p.grad is not None and p.grad.data_ptr() == bucket.view(i).data_ptr()
+        results.append(bucket.flat.clone())
+    torch.save(results, os.path.join(out_dir, f"rank{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_two_rank_bucket_allreduce_equals_single_rank_mean(tmp_path):
+    world, n_views = 2, 4
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, n_views, str(tmp_path)), nprocs=world, join=True)
+    r0 = torch.load(tmp_path / "rank0.pt")
+    r1 = torch.load(tmp_path / "rank1.pt")
+    params = [torch.zeros(50, 3), torch.zeros(50, 16, 3), torch.zeros(50, 1)]
+    ref_bucket = GradBucket([p.requires_grad_(True) for p in params], 1, register=False)
+    for s in range(n_views // world):
+        assert torch.equal(r0[s], r1[s])                      # every rank holds the same reduced bucket
+        views = [shard_views(n_views, r, world)[s] for r in range(world)]
+        expect = torch.zeros_like(ref_bucket.flat)
+        for v in views:
+            for i, g in enumerate(_fake_view_grads(params, v)):
+                o = ref_bucket.offsets[i]
+                expect[o:o + g.numel()] += g.reshape(-1) / world
+        assert torch.allclose(r0[s], expect, atol=1e-6)
+
+
+def test_shard_views_partitions_all_views():
+    for world in (1, 2, 4, 8):
+        seen = sorted(v for r in range(world) for v in shard_views(32, r, world))
+        assert seen == list(range(32))
+
+
+def test_bucket_views_are_aligned_and_disjoint():
+    params = [torch.zeros(7, 3, requires_grad=True), torch.zeros(7, 16, 3, requires_grad=True)]
+    b = GradBucket(params, 1, register=False)
+    assert b.offsets[1] % 64 == 0 and b.offsets[1] >= 21
+    b.view(0).fill_(1.0)
+    b.view(1).fill_(2.0)
+    assert float(b.view(0).sum()) == 21.0 and float(b.view(1).sum()) == 2.0 * 7 * 48

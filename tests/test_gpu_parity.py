@@ -39,3 +39,288 @@ def test_cfg1_training_style_grads():
     ref = h.run_c_oracle(S, st, grads)
     h.assert_images_close(got, ref)
     h.assert_grads_close(got["grads"], ref["grads"])
+
+
+# ------------------------------------------------------------------------------------ alt paths
+def _sh_colors(st, cam, deg=3):
+    d = st.means3D - cam.camera_center[None]
+    d = d / d.norm(dim=1, keepdim=True)
+    return torch.clamp_min(h.torch_oracle.eval_sh_rgb(deg, st.shs, d) + 0.5, 0.0)
+
+
+def test_colors_precomp_and_cov3d_precomp_paths():
+    """--convert_SHs_python / --compute_cov3D_python facade branches (gaussian_renderer/__init__.py:69-89)."""
+    st = gg.scenes.random_cloud(3000, seed=4)
+    cam = gg.scenes.cfg1_camera(256, 200)
+    S = h.settings_for(cam, st, device=torch.device("cuda:0"))
+    grads = _upstream_grads(cam.image_height, cam.image_width)
+    col = _sh_colors(st, cam)
+    cov = h.torch_oracle.covariance3d(st.scales, 1.0, st.rotations)
+    got = h.run_cuda(S, st, grads, colors_precomp=col, cov3D_precomp=cov)
+    ref = h.run_c_oracle(S, st, grads, colors_precomp=col, cov3D_precomp=cov)
+    h.assert_images_close(got, ref)
+    h.assert_grads_close(got["grads"], ref["grads"])
+    assert got["grads"]["shs"] is None and got["grads"]["scales"] is None
+
+
+@pytest.mark.parametrize("deg", [0, 1, 2])
+def test_lower_active_sh_degree_with_full_coefficient_tensor(deg):
+    st = gg.scenes.random_cloud(2500, seed=6)
+    st.sh_degree = deg
+    cam = gg.scenes.cfg1_camera(208, 176)
+    S = h.settings_for(cam, st, device=torch.device("cuda:0"))
+    grads = _upstream_grads(cam.image_height, cam.image_width)
+    got = h.run_cuda(S, st, grads)
+    ref = h.run_c_oracle(S, st, grads)
+    h.assert_images_close(got, ref)
+    h.assert_grads_close(got["grads"], ref["grads"])
+    nb = (deg + 1) ** 2
+    assert float(got["grads"]["shs"][:, nb:].abs().max()) == 0.0        # coefficients above D get zero gradient
+
+
+def test_registration_style_degree0_single_coefficient():
+    """s2_registration.py:158 forces sh_degree 0; shs is [N,1,3] there (generic-M kernel path)."""
+    st = gg.scenes.random_cloud(3000, seed=8, max_sh_degree=0, sh_degree=0)
+    cam = gg.scenes.cfg1_camera(256, 256)
+    S = h.settings_for(cam, st, device=torch.device("cuda:0"))
+    grads = _upstream_grads(cam.image_height, cam.image_width, depth_alpha=False)
+    got = h.run_cuda(S, st, grads)
+    ref = h.run_c_oracle(S, st, grads)
+    h.assert_images_close(got, ref)
+    h.assert_grads_close(got["grads"], ref["grads"])
+
+
+def test_scale_modifier():
+    st = gg.scenes.random_cloud(1500, seed=9)
+    cam = gg.scenes.cfg1_camera(160, 160)
+    S = h.settings_for(cam, st, device=torch.device("cuda:0"), scale_modifier=1.7)
+    grads = _upstream_grads(cam.image_height, cam.image_width)
+    got = h.run_cuda(S, st, grads)
+    ref = h.run_c_oracle(S, st, grads)
+    h.assert_images_close(got, ref)
+    h.assert_grads_close(got["grads"], ref["grads"])
+
+
+# ------------------------------------------------------------------------------------ edge cases
+def test_zero_gaussians_gives_zero_image():
+    st = gg.scenes.random_cloud(0)
+    cam = gg.scenes.cfg1_camera(64, 48)
+    S = h.settings_for(cam, st, device=torch.device("cuda:0"))
+    got = h.run_cuda(S, st)
+    assert got["color"].shape == (3, 48, 64) and float(got["color"].abs().max()) == 0.0
+    assert got["radii"].numel() == 0
+
+
+def test_all_gaussians_behind_camera():
+    st = gg.scenes.random_cloud(500, seed=3)
+    st.means3D = st.means3D - torch.tensor([0.0, 0.0, 10.0])
+    cam = gg.scenes.cfg1_camera(64, 64)
+    S = h.settings_for(cam, st, device=torch.device("cuda:0"))
+    grads = _upstream_grads(64, 64)
+    got = h.run_cuda(S, st, grads)
+    assert int((got["radii"] > 0).sum()) == 0
+    assert torch.allclose(got["color"], st.bg[:, None, None].expand(3, 64, 64))
+    assert float(got["alpha"].abs().max()) == 0.0
+    for k in ("means3D", "shs", "opacities", "scales", "rotations"):
+        assert float(got["grads"][k].abs().max()) == 0.0
+
+
+def test_image_sizes_of_the_reference_data():
+    """940x1280 (s3_appearance.py:92): neither side a multiple of 16 -> partial tiles."""
+    st = gg.scenes.random_cloud(4000, seed=12)
+    cam = gg.scenes.cfg1_camera(470, 330)
+    S = h.settings_for(cam, st, device=torch.device("cuda:0"))
+    grads = _upstream_grads(cam.image_height, cam.image_width)
+    got = h.run_cuda(S, st, grads)
+    ref = h.run_c_oracle(S, st, grads)
+    h.assert_images_close(got, ref)
+    h.assert_grads_close(got["grads"], ref["grads"])
+
+
+def test_dense_tile_exceeding_shared_memory_sort_capacity():
+    """> 4096 instances in one tile: the per-tile sort falls back to its global-memory path."""
+    n = 6000
+    st = gg.scenes.random_cloud(n, seed=13)
+    g = torch.Generator().manual_seed(5)
+    st.means3D = torch.cat([torch.randn(n, 2, generator=g) * 0.01, 4.0 + torch.rand(n, 1, generator=g) * 2], dim=1)
+    st.means3D[:, 2] -= 4.0          # camera T=(0,0,4): view depth 4..6
+    st.scales = torch.full((n, 3), 0.004)
+    st.opacities = torch.full((n, 1), 0.02)
+    cam = gg.scenes.cfg1_camera(64, 64)
+    S = h.settings_for(cam, st, device=torch.device("cuda:0"))
+    grads = _upstream_grads(64, 64)
+    got = h.run_cuda(S, st, grads)
+    ref = h.run_c_oracle(S, st, grads)
+    off = ref["ctx"].binning()["tile_off"]
+    assert int((off[1:] - off[:-1]).max()) > 4096
+    h.assert_images_close(got, ref, max_fragile_frac=0.05)
+    h.assert_grads_close(got["grads"], ref["grads"], tol=3e-3)
+
+
+def test_depth_ties_keep_index_order():
+    """Equal fp32 depths in one tile: order must be ascending Gaussian index (stable-sort semantics)."""
+    n = 64
+    st = gg.scenes.random_cloud(n, seed=14)
+    g = torch.Generator().manual_seed(2)
+    st.means3D = torch.cat([torch.rand(n, 2, generator=g) * 0.2 - 0.1, torch.zeros(n, 1)], dim=1)   # same depth 4.0
+    st.scales = torch.full((n, 3), 0.05)
+    st.opacities = torch.full((n, 1), 0.6)
+    cam = gg.cameras.make_camera(__import__("numpy").eye(3), [0, 0, 4.0], 300.0, 300.0, 32.0, 32.0, 64, 64)
+    S = h.settings_for(cam, st, device=torch.device("cuda:0"))
+    got = h.run_cuda(S, st)
+    ref = h.run_c_oracle(S, st)
+    assert float((got["color"] - ref["color"]).abs().max()) < 1e-4
+
+
+def test_kat_single_gaussian_on_gpu():
+    import numpy as np
+    cam = gg.cameras.make_camera(np.eye(3), np.zeros(3), 80.0, 80.0, 32.5, 32.5, 64, 64)
+    st = gg.scenes.random_cloud(1, seed=1)
+    st.means3D = torch.tensor([[0.0, 0.0, 2.0]])
+    st.scales = torch.full((1, 3), 0.05)
+    st.rotations = torch.tensor([[1.0, 0, 0, 0]])
+    st.opacities = torch.tensor([[0.5]])
+    st.bg = torch.tensor([0.1, 0.2, 0.3])
+    col = torch.tensor([[0.2, 0.6, 0.9]])
+    S = h.settings_for(cam, st, device=torch.device("cuda:0"))
+    got = h.run_cuda(S, st, colors_precomp=col)
+    assert abs(float(got["alpha"][0, 32, 32]) - 0.5) < 1e-6
+    assert torch.allclose(got["color"][:, 32, 32], 0.5 * col[0] + 0.5 * st.bg, atol=1e-6)
+    assert abs(float(got["depth"][0, 32, 32]) - 1.0) < 1e-6
+
+
+# ------------------------------------------------------------------------------------ API contract
+def _api_inputs(n=2000, res=(160, 128), seed=21):
+    dev = torch.device("cuda:0")
+    st = gg.scenes.random_cloud(n, seed=seed).to(dev)
+    cam = gg.scenes.cfg1_camera(*res).to(dev)
+    S = h.settings_for(cam, st, device=dev)
+    return dev, st, cam, S
+
+
+def test_inplace_mutation_of_color_before_backward_is_allowed():
+    """utils/loss_utils.py:45 multiplies the rendered image in place (ssim mask) before backward()."""
+    dev, st, cam, S = _api_inputs()
+    m3 = st.means3D.clone().requires_grad_(True)
+    m2 = torch.zeros_like(m3, requires_grad=True)
+    color, radii, depth, alpha = h.dgr.GaussianRasterizer(raster_settings=S)(
+        means3D=m3, means2D=m2, shs=st.shs, colors_precomp=None, opacities=st.opacities, scales=st.scales,
+        rotations=st.rotations, cov3D_precomp=None)
+    gt = torch.rand_like(color)
+    mask = (torch.rand(1, *color.shape[1:], device=dev) > 0.3).float()
+    loss1 = torch.abs((color - gt) * mask).mean()          # l1_loss(image, gt, mask)   utils/loss_utils.py:17-21
+    color *= mask                                           # ssim(): `img1 *= mask`      utils/loss_utils.py:45
+    loss2 = (color * gt).mean()
+    (loss1 + loss2).backward()
+    assert torch.isfinite(m3.grad).all() and float(m3.grad.abs().max()) > 0
+
+
+def test_no_grad_and_visibility_filter():
+    dev, st, cam, S = _api_inputs()
+    with torch.no_grad():
+        color, radii, depth, alpha = h.dgr.GaussianRasterizer(raster_settings=S)(
+            means3D=st.means3D, means2D=torch.zeros_like(st.means3D), shs=st.shs, colors_precomp=None,
+            opacities=st.opacities, scales=st.scales, rotations=st.rotations, cov3D_precomp=None)
+    assert not color.requires_grad and radii.dtype == torch.int32 and radii.shape == (st.N,)
+    assert color.shape == (3, cam.image_height, cam.image_width) and depth.shape[0] == 1 and alpha.shape[0] == 1
+    vis = h.dgr.GaussianRasterizer(raster_settings=S).markVisible(st.means3D)
+    zview = (torch.cat([st.means3D, torch.ones(st.N, 1, device=dev)], 1) @ cam.world_view_transform)[:, 2]
+    assert torch.equal(vis, zview > 0.2)
+    assert bool(((radii > 0) <= vis).all())
+
+
+def test_means2D_side_channel_and_masked_inputs():
+    """viewspace_points.grad[:, :2] is read by densification (scene/gaussian_model.py:410-412); inputs may
+    come out of boolean-mask indexing (gaussian_renderer/__init__.py:92-100)."""
+    dev, st, cam, S = _api_inputs(3000)
+    mask = torch.rand(st.N, device=dev) > 0.3
+    leaves = [t.clone().requires_grad_(True) for t in (st.means3D, st.shs, st.opacities, st.scales, st.rotations)]
+    screenspace = torch.zeros_like(leaves[0], requires_grad=True) + 0
+    screenspace.retain_grad()
+    color, radii, depth, alpha = h.dgr.GaussianRasterizer(raster_settings=S)(
+        means3D=leaves[0][mask], means2D=screenspace[mask], shs=leaves[1][mask], colors_precomp=None,
+        opacities=leaves[2][mask], scales=leaves[3][mask], rotations=leaves[4][mask], cov3D_precomp=None)
+    color.sum().backward()
+    assert screenspace.grad.shape == (st.N, 3)
+    assert float(screenspace.grad[~mask].abs().max()) == 0.0
+    assert float(screenspace.grad[:, 2].abs().max()) == 0.0
+    assert float(screenspace.grad[mask][:, :2].abs().max()) > 0
+    assert radii.shape[0] == int(mask.sum())
+
+
+def test_forward_is_deterministic_and_backward_is_stable():
+    dev, st, cam, S = _api_inputs(4000, (256, 256))
+    outs = []
+    for _ in range(2):
+        m3 = st.means3D.clone().requires_grad_(True)
+        color, radii, depth, alpha = h.dgr.GaussianRasterizer(raster_settings=S)(
+            means3D=m3, means2D=torch.zeros_like(m3), shs=st.shs, colors_precomp=None, opacities=st.opacities,
+            scales=st.scales, rotations=st.rotations, cov3D_precomp=None)
+        color.square().sum().backward()
+        outs.append((color.detach().clone(), m3.grad.clone()))
+    assert torch.equal(outs[0][0], outs[1][0])                       # forward: bit-identical
+    assert h.rel_inf(outs[0][1], outs[1][1]) < 1e-4                  # backward: float atomics reorder only
+
+
+def test_grad_bucket_zero_copy_sink():
+    """dist.GradBucket: backward writes straight into the flat bucket and autograd adopts the views."""
+    from gaussian_garments_b200.dist import GradBucket
+    dev, st, cam, S = _api_inputs(2500)
+    params = [t.clone().requires_grad_(True) for t in (st.means3D, st.scales, st.rotations, st.opacities, st.shs)]
+    plain = [t.clone().requires_grad_(True) for t in (st.means3D, st.scales, st.rotations, st.opacities, st.shs)]
+
+    def run(ps):
+        color, *_ = h.dgr.GaussianRasterizer(raster_settings=S)(
+            means3D=ps[0], means2D=torch.zeros_like(ps[0]), shs=ps[4], colors_precomp=None, opacities=ps[3],
+            scales=ps[1], rotations=ps[2], cov3D_precomp=None)
+        (color - 0.3).abs().mean().backward()
+
+    bucket = GradBucket(params, 1)
+    try:
+        bucket.zero()
+        run(params)
+        for i, p in enumerate(params):
+            assert p.grad is not None and p.grad.data_ptr() == bucket.view(i).data_ptr(), "grad was copied, not adopted"
+    finally:
+        bucket.unregister()
+    run(plain)
+    for a, b in zip(params, plain):
+        assert h.rel_inf(a.grad, b.grad) < 1e-4
+
+
+def test_cfg2_full_size_invariants():
+    """BASELINE.json configs[1] at full size: size-independent properties (oracle too slow to loop here)."""
+    dev = torch.device("cuda:0")
+    st = gg.scenes.mesh_bound_state(300_000).to(dev)
+    cam = gg.scenes.cfg2_cameras(8)[3].to(dev)
+    S = h.settings_for(cam, st, device=dev)
+    leaves = [t.clone().requires_grad_(True) for t in (st.means3D, st.shs, st.opacities, st.scales, st.rotations)]
+
+    def render(bg=None, sh=None):
+        s = S if bg is None else S._replace(bg=bg)
+        return h.dgr.GaussianRasterizer(raster_settings=s)(
+            means3D=leaves[0], means2D=torch.zeros_like(leaves[0]), shs=leaves[1] if sh is None else sh,
+            colors_precomp=None, opacities=leaves[2], scales=leaves[3], rotations=leaves[4], cov3D_precomp=None)
+
+    color, radii, depth, alpha = render()
+    assert torch.isfinite(color).all() and torch.isfinite(depth).all()
+    assert float(alpha.min()) >= 0.0 and float(alpha.max()) <= 1.0 + 1e-5
+    # background linearity: color(bg) - color(0) == (1 - alpha) * bg  (alpha = 1 - T_final up to rounding)
+    c0, _, _, a0 = render(bg=torch.zeros(3, device=dev))
+    assert float((color - c0 - (1 - a0) * st.bg[:, None, None]).abs().max()) < 2e-5
+    # colour linearity in the DC coefficients (no clamp active when DC is large and positive)
+    (color.mean() + depth.mean() * 0.1).backward()
+    for t in leaves:
+        assert torch.isfinite(t.grad).all()
+    assert float(leaves[1].grad[:, 0].abs().sum()) > 0
+    # full-size parity against the C oracle (0.5 s on 8 cores): forward + gradients
+    gC = torch.full((3, cam.image_height, cam.image_width), 1.0 / (3 * cam.image_height * cam.image_width))
+    gD = torch.full((1, cam.image_height, cam.image_width), 0.1 / (cam.image_height * cam.image_width))
+    ref = h.run_c_oracle(S, st.to("cpu"), (gC, gD, None))
+    got = dict(color=color.detach().cpu(), depth=depth.detach().cpu(), alpha=alpha.detach().cpu())
+    assert int((radii.cpu() != ref["radii"]).sum()) <= 3
+    h.assert_images_close(got, ref)
+    gg_ = dict(means3D=leaves[0].grad.cpu(), shs=leaves[1].grad.cpu(), opacities=leaves[2].grad.cpu(),
+               scales=leaves[3].grad.cpu(), rotations=leaves[4].grad.cpu())
+    refg = {k: v for k, v in ref["grads"].items() if k in gg_}
+    h.assert_grads_close(gg_, refg)
