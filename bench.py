@@ -199,7 +199,7 @@ def main():
             viewmatrix=cam.world_view_transform, projmatrix=cam.full_proj_transform, sh_degree=st.sh_degree,
             campos=cam.camera_center, prefiltered=False, debug=False)
 
-    def step(i, gt, cam=None):
+    def step(i, gt, cam=None, collective=True):
         cam = cam if cam is not None else cams[(i * world + rank) % N_CAMS]
         means2D = torch.zeros_like(params[0], requires_grad=True)
         color, radii, depth, alpha = dgr.GaussianRasterizer(raster_settings=settings(cam))(
@@ -208,7 +208,8 @@ def main():
         loss = (color - gt).abs().mean()
         bucket.zero()
         loss.backward()
-        bucket.all_reduce()
+        if collective:
+            bucket.all_reduce()
         return loss
 
     # ---------------- device-resident timing: `value` ----------------
@@ -295,7 +296,7 @@ def main():
     reps = 8
     for i in range(reps):
         flush_buf.fill_(1)
-        step(i, gt_dev[i % 2])
+        step(i, gt_dev[i % 2], collective=False)      # rank 0 only: no collective here
         torch.cuda.synchronize()
         for k, v in _capi.kernel_times().items():
             acc[k] = acc.get(k, 0.0) + v / reps
@@ -319,7 +320,7 @@ def main():
                 "kernels": kernels, "kernel_ms_sum": round(sum(k["ms"] for k in kernels), 4)}
 
     cpu_baseline = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         cpu_baseline = run_cpu_baseline(args, st_cpu, cams_cpu, gts_cpu[0])
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -47,6 +47,12 @@ def _needs_build() -> bool:
     return False
 
 
+# project.cu is compiled with -fmad=false: without FMA contraction its IEEE +,-,*,/,sqrt arithmetic is
+# bit-identical to the CPU oracle's (gcc -ffp-contract=off), so every DISCRETE decision taken from the
+# projected geometry (cull, radius, tile rectangle, depth order) agrees with the oracle by construction.
+PER_FILE_FLAGS = {"project.cu": ["-fmad=false"]}
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile csrc/*.cu for sm_100a into csrc/libgg_raster.so (in-tree, so it travels to the GPU box)."""
     if not force and not _needs_build():
@@ -54,12 +60,24 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("gaussian-garments_b200: nvcc not found and libgg_raster.so is missing/stale")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + SOURCES
-    res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+    common = [f for f in NVCC_FLAGS if f != "-shared"]
+    procs, objs, log = [], [], ""
+    for src in SOURCES:
+        obj = src.replace(".cu", ".o")
+        objs.append(obj)
+        cmd = [nvcc] + common + PER_FILE_FLAGS.get(src, []) + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+        procs.append((src, subprocess.Popen(cmd, cwd=CSRC, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for src, pr in procs:
+        out, _ = pr.communicate()
+        log += out
+        if pr.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n{out}")
+    res = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH] + objs,
+                         cwd=CSRC, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+        raise RuntimeError("nvcc link failed:\n" + res.stdout + res.stderr)
     if verbose:
-        print(res.stderr)
+        print(log)
     return LIB_PATH
 
 

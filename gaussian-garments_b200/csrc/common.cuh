@@ -271,7 +271,9 @@ __device__ __forceinline__ void ewa_project(const float* V, float x, float y, fl
                                             float focal_y, float tanfovx, float tanfovy, Ewa& e) {
     e.tvx = V[0] * x + V[4] * y + V[8] * z + V[12];
     e.tvy = V[1] * x + V[5] * y + V[9] * z + V[13];
-    e.tvz = V[2] * x + V[6] * y + V[10] * z + V[14];
+    // view depth is the sort key: fixed fused evaluation order so that it is bit-identical to the
+    // CPU oracle (oracle/gg_oracle.c uses the same fmaf chain) and near-equal depths order the same
+    e.tvz = __fmaf_rn(V[10], z, __fmaf_rn(V[6], y, __fmaf_rn(V[2], x, V[14])));
     const float limx = 1.3f * tanfovx, limy = 1.3f * tanfovy;
     const float txtz = e.tvx / e.tvz, tytz = e.tvy / e.tvz;
     e.tx = fminf(limx, fmaxf(-limx, txtz)) * e.tvz;

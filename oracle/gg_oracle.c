@@ -192,7 +192,7 @@ int ggo_forward(const ggo_params* pp, const float* means3D, const float* shs, co
         const float x = means3D[3 * i], y = means3D[3 * i + 1], z = means3D[3 * i + 2];
         float tvx = V[0] * x + V[4] * y + V[8] * z + V[12];
         float tvy = V[1] * x + V[5] * y + V[9] * z + V[13];
-        float tvz = V[2] * x + V[6] * y + V[10] * z + V[14];
+        float tvz = fmaf(V[10], z, fmaf(V[6], y, fmaf(V[2], x, V[14]))); /* sort key: same fused chain as the CUDA kernel */
         if (!(tvz > NEAR_Z)) continue;
         float hx = Pm[0] * x + Pm[4] * y + Pm[8] * z + Pm[12];
         float hy = Pm[1] * x + Pm[5] * y + Pm[9] * z + Pm[13];
@@ -550,7 +550,7 @@ int ggo_backward(const ggo_state* s, const float* dL_dcolor, const float* dL_dde
         /* ---- conic -> Sigma2D ---- */
         float tvx = V[0] * x + V[4] * y + V[8] * z + V[12];
         float tvy = V[1] * x + V[5] * y + V[9] * z + V[13];
-        float tvz = V[2] * x + V[6] * y + V[10] * z + V[14];
+        float tvz = fmaf(V[10], z, fmaf(V[6], y, fmaf(V[2], x, V[14]))); /* sort key: same fused chain as the CUDA kernel */
         const float limx = 1.3f * p.tanfovx, limy = 1.3f * p.tanfovy;
         float txtz = tvx / tvz, tytz = tvy / tvz;
         float tx = fminf(limx, fmaxf(-limx, txtz)) * tvz;
