@@ -3,10 +3,12 @@
 // One CTA per tile, one pixel per thread.  The tile's packed records are streamed BACKWARDS
 // (from the last contributor of any pixel in the tile) through a 2-stage bulk-TMA/mbarrier ring.
 // Per Gaussian every thread forms its 10 partial derivatives; a warp that has no contributing
-// pixel skips the Gaussian (one ballot), otherwise the warp reduces the 10 values with shuffles
-// and lane 0 parks them in a per-warp shared-memory slot.  After a batch the CTA folds the 8 warp
-// slots and issues at most three vector reductions (float4, float4, float2 red.global) per
-// (tile, Gaussian) instance -- instead of upstream's ~10 scalar atomics per (pixel, Gaussian).
+// pixel skips the Gaussian (one ballot).  Otherwise the warp reduces the 10 values with a
+// TRANSPOSED butterfly (reduce-scatter: 5+3+2+1+1 = 12 shuffles instead of 10 x 5 = 50), after which
+// ten lanes each hold one finished sum and park it in the warp's shared-memory slot with a single
+// predicated store.  After a batch the CTA folds the 8 warp slots and issues at most three vector
+// reductions (red.global.add.v4.f32 x2, .v2.f32 x1) per (tile, Gaussian) instance -- instead of
+// upstream's ~10 scalar atomics per (pixel, Gaussian).
 #include "common.cuh"
 
 namespace gg {
@@ -15,6 +17,40 @@ constexpr int BWD_BATCH = 64;
 constexpr int BWD_STAGES = 2;
 constexpr int BWD_WARPS = TILE_PIX / 32;
 constexpr int ACC_STRIDE = 12;   // 10 used; keeps float4 alignment
+
+// Reduce-scatter of 10 per-lane values over the 32 lanes of a warp.  On return lane L holds the
+// warp-wide sum of value `slot` (or nothing when slot < 0); lanes 2k and 2k+1 hold the same one.
+__device__ __forceinline__ float warp_reduce_scatter10(const float* v, int lane, int& slot) {
+    const unsigned FULL = 0xffffffffu;
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+    float r0, r1, r2, r3, r4;
+    {   // xor 16: lower half keeps values 0..4, upper half keeps 5..9
+        r0 = (b4 ? v[5] : v[0]) + __shfl_xor_sync(FULL, b4 ? v[0] : v[5], 16);
+        r1 = (b4 ? v[6] : v[1]) + __shfl_xor_sync(FULL, b4 ? v[1] : v[6], 16);
+        r2 = (b4 ? v[7] : v[2]) + __shfl_xor_sync(FULL, b4 ? v[2] : v[7], 16);
+        r3 = (b4 ? v[8] : v[3]) + __shfl_xor_sync(FULL, b4 ? v[3] : v[8], 16);
+        r4 = (b4 ? v[9] : v[4]) + __shfl_xor_sync(FULL, b4 ? v[4] : v[9], 16);
+    }
+    float s0, s1, s2;
+    {   // xor 8: b3 = 0 keeps {r0,r1,r2}, b3 = 1 keeps {r3,r4,-}
+        s0 = (b3 ? r3 : r0) + __shfl_xor_sync(FULL, b3 ? r0 : r3, 8);
+        s1 = (b3 ? r4 : r1) + __shfl_xor_sync(FULL, b3 ? r1 : r4, 8);
+        s2 = (b3 ? 0.f : r2) + __shfl_xor_sync(FULL, b3 ? r2 : 0.f, 8);
+    }
+    float t0, t1;
+    {   // xor 4: b2 = 0 keeps {s0,s1}, b2 = 1 keeps {s2,-}
+        t0 = (b2 ? s2 : s0) + __shfl_xor_sync(FULL, b2 ? s0 : s2, 4);
+        t1 = (b2 ? 0.f : s1) + __shfl_xor_sync(FULL, b2 ? s1 : 0.f, 4);
+    }
+    float u = (b1 ? t1 : t0) + __shfl_xor_sync(FULL, b1 ? t0 : t1, 2);   // xor 2
+    u += __shfl_xor_sync(FULL, u, 1);                                    // xor 1
+    // which value did this lane end up with?
+    int within;
+    if (!b3) within = !b2 ? (b1 ? 1 : 0) : (b1 ? -1 : 2);
+    else     within = !b2 ? (b1 ? 4 : 3) : -1;
+    slot = within < 0 ? -1 : (b4 ? 5 : 0) + within;
+    return u;
+}
 
 __global__ void __launch_bounds__(TILE_PIX)
 blend_bwd_kernel(const uint32_t* __restrict__ tile_offset, const float4* __restrict__ p0,
@@ -83,67 +119,62 @@ blend_bwd_kernel(const uint32_t* __restrict__ tile_offset, const float4* __restr
         if (dL_ddepth) gD = dL_ddepth[pid];
         if (dL_dalpha) gA = dL_dalpha[pid];
     }
-    const float bg_dot = bg[0] * gC0 + bg[1] * gC1 + bg[2] * gC2;
+    const float bgT = -T_final * (bg[0] * gC0 + bg[1] * gC1 + bg[2] * gC2);
     float ac0 = 0.f, ac1 = 0.f, ac2 = 0.f, acd = 0.f, aca = 0.f;     // values "behind"
     float last_alpha = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, ld = 0.f;
-    const float half_W = 0.5f * W, half_H = 0.5f * H;
+    const float kx = LN2 * 0.5f * W, ky = LN2 * 0.5f * H;           // d/dx of 2^p2 carries ln 2
+    const uint32_t acc_warp = smem_u32(&acc[warp][0][0]);
 
     for (int q = 0; q < nb; q++) {
         const int st = q % BWD_STAGES;
         const int b = nb - 1 - q;
         const int cnt = min(BWD_BATCH, (int)n - b * BWD_BATCH);
         mbar_wait(&full[st], (uint32_t)(q / BWD_STAGES) & 1u);
+        const uint32_t r0 = smem_u32(&s0[st][0]), r1 = smem_u32(&s1[st][0]), r2 = smem_u32(&s2[st][0]);
         for (int j = cnt - 1; j >= 0; j--) {
             const uint32_t idx = (uint32_t)(b * BWD_BATCH + j);
-            bool contrib = idx < my_n;
-            float4 a, c;
-            float dx = 0.f, dy = 0.f, G = 0.f, alpha = 0.f;
-            if (contrib) {
-                a = s0[st][j];
-                c = s1[st][j];
-                dx = a.x - fx;
-                dy = a.y - fy;
-                const float power = -0.5f * (a.z * dx * dx + c.x * dy * dy) - a.w * dx * dy;
-                G = __expf(power);
-                alpha = fminf(ALPHA_MAX, c.y * G);
-                contrib = (power <= 0.f) && (alpha >= ALPHA_MIN);
-            }
+            const float4 a = lds128(r0 + 16u * j);
+            const float4 c = lds128(r1 + 16u * j);
+            const float dx = a.x - fx, dy = a.y - fy;
+            const float e2 = dx * (a.z * dx + a.w * dy) + (c.x * dy) * dy;     // log2-domain exponent
+            const float G = ex2_approx(e2);
+            const float alpha = fminf(ALPHA_MAX, c.y * G);
+            const bool contrib = (idx < my_n) && (e2 <= 0.f) && (alpha >= ALPHA_MIN);
             if (!__any_sync(0xffffffffu, contrib)) continue;
-            float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f, v4 = 0.f, v5 = 0.f, v6 = 0.f, v7 = 0.f, v8 = 0.f, v9 = 0.f;
+            float v[10];
+#pragma unroll
+            for (int k = 0; k < 10; k++) v[k] = 0.f;
             if (contrib) {
-                T = T / (1.f - alpha);
+                const float rinv = rcp_approx(1.f - alpha);
+                T *= rinv;
                 const float w = alpha * T;
-                const float4 col = s2[st][j];
-                float dL_da = 0.f;
-                ac0 = last_alpha * lc0 + (1.f - last_alpha) * ac0; lc0 = col.x; dL_da += (col.x - ac0) * gC0;
-                ac1 = last_alpha * lc1 + (1.f - last_alpha) * ac1; lc1 = col.y; dL_da += (col.y - ac1) * gC1;
-                ac2 = last_alpha * lc2 + (1.f - last_alpha) * ac2; lc2 = col.z; dL_da += (col.z - ac2) * gC2;
-                acd = last_alpha * ld + (1.f - last_alpha) * acd;  ld = c.z;   dL_da += (c.z - acd) * gD;
-                aca = last_alpha + (1.f - last_alpha) * aca;                   dL_da += (1.f - aca) * gA;
-                dL_da *= T;
+                const float4 col = lds128(r2 + 16u * j);
+                const float oml = 1.f - last_alpha;
+                float dL_da;
+                ac0 = last_alpha * lc0 + oml * ac0; lc0 = col.x; dL_da = (col.x - ac0) * gC0;
+                ac1 = last_alpha * lc1 + oml * ac1; lc1 = col.y; dL_da += (col.y - ac1) * gC1;
+                ac2 = last_alpha * lc2 + oml * ac2; lc2 = col.z; dL_da += (col.z - ac2) * gC2;
+                acd = last_alpha * ld + oml * acd;  ld = c.z;    dL_da += (c.z - acd) * gD;
+                aca = last_alpha + oml * aca;                    dL_da += (1.f - aca) * gA;
+                dL_da = dL_da * T + bgT * rinv;
                 last_alpha = alpha;
-                dL_da += (-T_final / (1.f - alpha)) * bg_dot;
-                const float dL_dG = c.y * dL_da;
-                const float gdx = G * dx, gdy = G * dy;
-                v0 = dL_dG * (-gdx * a.z - gdy * a.w) * half_W;
-                v1 = dL_dG * (-gdy * c.x - gdx * a.w) * half_H;
-                v2 = -0.5f * gdx * dx * dL_dG;
-                v3 = -gdx * dy * dL_dG;
-                v4 = -0.5f * gdy * dy * dL_dG;
-                v5 = G * dL_da;
-                v6 = w * gC0;
-                v7 = w * gC1;
-                v8 = w * gC2;
-                v9 = w * gD;
+                const float X = c.y * dL_da * G;          // dL/dG * G
+                v[0] = X * (2.f * a.z * dx + a.w * dy) * kx;
+                v[1] = X * (2.f * c.x * dy + a.w * dx) * ky;
+                const float Xdx = X * dx;
+                v[2] = -0.5f * Xdx * dx;
+                v[3] = -Xdx * dy;
+                v[4] = -0.5f * X * dy * dy;
+                v[5] = G * dL_da;
+                v[6] = w * gC0;
+                v[7] = w * gC1;
+                v[8] = w * gC2;
+                v[9] = w * gD;
             }
-            v0 = warp_sum(v0); v1 = warp_sum(v1); v2 = warp_sum(v2); v3 = warp_sum(v3); v4 = warp_sum(v4);
-            v5 = warp_sum(v5); v6 = warp_sum(v6); v7 = warp_sum(v7); v8 = warp_sum(v8); v9 = warp_sum(v9);
-            if (lane == 0) {
-                float4* slot = reinterpret_cast<float4*>(&acc[warp][j][0]);
-                slot[0] = make_float4(v0, v1, v2, v3);
-                slot[1] = make_float4(v4, v5, v6, v7);
-                *reinterpret_cast<float2*>(&acc[warp][j][8]) = make_float2(v8, v9);
-            }
+            int slot;
+            const float sum = warp_reduce_scatter10(v, lane, slot);
+            if (slot >= 0 && !(lane & 1))
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(acc_warp + 4u * (uint32_t)(j * ACC_STRIDE + slot)), "f"(sum) : "memory");
         }
         __syncthreads();   // warp slots complete
         // fold the 8 warp slots; 3 work items (float4, float4, float2) per record
@@ -154,10 +185,10 @@ blend_bwd_kernel(const uint32_t* __restrict__ tile_offset, const float4* __restr
                 float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                 for (int w = 0; w < BWD_WARPS; w++) {
-                    float4* slot = reinterpret_cast<float4*>(&acc[w][j][4 * part]);
-                    const float4 q4 = *slot;
+                    float4* sl = reinterpret_cast<float4*>(&acc[w][j][4 * part]);
+                    const float4 q4 = *sl;
                     sum.x += q4.x; sum.y += q4.y; sum.z += q4.z; sum.w += q4.w;
-                    *slot = make_float4(0.f, 0.f, 0.f, 0.f);
+                    *sl = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
                 if (sum.x != 0.f || sum.y != 0.f || sum.z != 0.f || sum.w != 0.f)
                     atomicAdd(part == 0 ? &a0[id] : &a1[id], sum);
@@ -165,10 +196,10 @@ blend_bwd_kernel(const uint32_t* __restrict__ tile_offset, const float4* __restr
                 float2 sum = make_float2(0.f, 0.f);
 #pragma unroll
                 for (int w = 0; w < BWD_WARPS; w++) {
-                    float2* slot = reinterpret_cast<float2*>(&acc[w][j][8]);
-                    const float2 q2 = *slot;
+                    float2* sl = reinterpret_cast<float2*>(&acc[w][j][8]);
+                    const float2 q2 = *sl;
                     sum.x += q2.x; sum.y += q2.y;
-                    *slot = make_float2(0.f, 0.f);
+                    *sl = make_float2(0.f, 0.f);
                 }
                 if (sum.x != 0.f || sum.y != 0.f) atomicAdd(&a2[id], sum);
             }

@@ -70,14 +70,16 @@ blend_fwd_kernel(const uint32_t* __restrict__ tile_offset, const float4* __restr
         // every iteration and doubles as the per-warp early-out.)
         {
             const int cnt = min(FWD_BATCH, (int)n - b * FWD_BATCH);
+            const uint32_t a0 = smem_u32(&s0[st][0]), a1 = smem_u32(&s1[st][0]), a2 = smem_u32(&s2[st][0]);
             for (int j = 0; j < cnt; j++) {
                 if (__all_sync(0xffffffffu, done)) break;
-                const float4 a = s0[st][j];
-                const float4 c = s1[st][j];
+                const float4 a = lds128(a0 + 16u * j);
+                const float4 c = lds128(a1 + 16u * j);
                 const float dx = a.x - fx, dy = a.y - fy;
-                const float power = -0.5f * (a.z * dx * dx + c.x * dy * dy) - a.w * dx * dy;
-                const float alpha = fminf(ALPHA_MAX, c.y * __expf(power));
-                bool ok = !done && power <= 0.f && alpha >= ALPHA_MIN;
+                // log2-domain exponent: A' dx^2 + B' dx dy + C' dy^2  (= power * log2 e)
+                const float p2 = dx * (a.z * dx + a.w * dy) + (c.x * dy) * dy;
+                const float alpha = fminf(ALPHA_MAX, c.y * ex2_approx(p2));
+                bool ok = !done && p2 <= 0.f && alpha >= ALPHA_MIN;
                 const float test_T = T * (1.f - alpha);
                 if (ok && test_T < T_STOP) {
                     done = true;
@@ -85,7 +87,7 @@ blend_fwd_kernel(const uint32_t* __restrict__ tile_offset, const float4* __restr
                 }
                 if (ok) {
                     const float w = alpha * T;
-                    const float4 col = s2[st][j];
+                    const float4 col = lds128(a2 + 16u * j);
                     C0 += col.x * w;
                     C1 += col.y * w;
                     C2 += col.z * w;

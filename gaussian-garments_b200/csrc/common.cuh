@@ -77,8 +77,8 @@ inline size_t image_layout(void* base, int64_t P, ImageWS* ws) {
 
 // Packed, depth-sorted per-instance records: three float4 planes so that a tile's list is three
 // contiguous 16-byte-aligned runs (1-D bulk-TMA friendly) and every store is fully coalesced.
-//   p0 = (px, py, conic.A, conic.B)   p1 = (conic.C, opacity, depth, gaussian id bits)
-//   p2 = (r, g, b, unused)
+//   p0 = (px, py, A', B')   p1 = (C', opacity, depth, gaussian id bits)   p2 = (r, g, b, unused)
+// with the conic pre-scaled into the log2 domain (A' = -0.5*log2e*A, B' = -log2e*B, C' = -0.5*log2e*C)
 struct RecordWS {
     float4* p0;
     float4* p1;
@@ -180,6 +180,29 @@ __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src_gmem)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// explicit shared-window loads: keeps the per-iteration address a single 32-bit add (the generic
+// path made ptxas rebuild the shared window base -- S2UR SR_CgaCtaId + 4 ULEA -- every iteration)
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float ex2_approx(float x) {   // 2^x, flush-to-zero (MUFU.EX2, no denormal fix-up)
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {   // MUFU.RCP
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// Packed records carry the conic pre-scaled into the log2 domain:
+//   A' = -0.5*log2(e)*A,  B' = -log2(e)*B,  C' = -0.5*log2(e)*C   =>   G = 2^(A' dx^2 + B' dx dy + C' dy^2)
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
 
 __device__ __forceinline__ float warp_sum(float v) {
     v += __shfl_xor_sync(0xffffffffu, v, 16);

@@ -12,6 +12,24 @@
 namespace gg {
 
 // ---------------------------------------------------------------------------------------------
+// Every lane walks its own tile rectangle; iteration k of all lanes is matched so that lanes hitting
+// the same tile issue ONE red.add of their population count.  Must be called by full warps.
+__device__ __forceinline__ void tile_count_aggregated(bool live, int x0, int y0, int x1, int y1, int gx,
+                                                      uint32_t* __restrict__ tile_count) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int nt = live ? (x1 - x0) * (y1 - y0) : 0;
+    const int max_nt = __reduce_max_sync(FULL, nt);
+    int tx = x0, ty = y0;
+    for (int k = 0; k < max_nt; k++) {
+        const bool valid = k < nt;
+        const int t = valid ? ty * gx + tx : -1 - lane;          // invalid lanes never match anyone
+        const unsigned grp = __match_any_sync(FULL, t);
+        if (valid && lane == __ffs(grp) - 1) atomicAdd(&tile_count[t], (uint32_t)__popc(grp));
+        if (++tx == x1) { tx = x0; ty++; }
+    }
+}
+
 __global__ void __launch_bounds__(256)
 project_kernel(int N, const float* __restrict__ means3D, const float* __restrict__ scales,
                const float* __restrict__ rotations, const float* __restrict__ cov3D_precomp,
@@ -22,8 +40,9 @@ project_kernel(int N, const float* __restrict__ means3D, const float* __restrict
     if (threadIdx.x < 16) cam[threadIdx.x] = viewmatrix[threadIdx.x];
     else if (threadIdx.x < 32) cam[threadIdx.x] = projmatrix[threadIdx.x - 16];
     __syncthreads();
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
+    const int i_raw = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in_range = i_raw < N;
+    const int i = in_range ? i_raw : N - 1;     // tail lanes recompute the last Gaussian but never store/count
     const float* V = cam;
     const float* Pm = cam + 16;
     const float x = means3D[3 * (size_t)i], y = means3D[3 * (size_t)i + 1], z = means3D[3 * (size_t)i + 2];
@@ -74,15 +93,18 @@ project_kernel(int N, const float* __restrict__ means3D, const float* __restrict
             }
         }
     }
-    radii[i] = rad_out;
-    g.xy[i] = xy;
-    g.depth[i] = depth;
-    g.conic_o[i] = con;
-    g.rect[i] = rect;
-    if (rad_out > 0) {
-        for (int ty = y0; ty < y1; ty++)
-            for (int tx = x0; tx < x1; tx++) atomicAdd(&tile_count[ty * gx + tx], 1u);
+    if (in_range) {
+        radii[i] = rad_out;
+        g.xy[i] = xy;
+        g.depth[i] = depth;
+        g.conic_o[i] = con;
+        g.rect[i] = rect;
+    } else {
+        rad_out = 0;
     }
+    // per-tile instance counts, warp-aggregated: neighbouring Gaussians (6 per mesh face) mostly hit the
+    // same tiles, so lanes that target the same counter elect one leader per iteration (match.any)
+    tile_count_aggregated(rad_out > 0, x0, y0, x1, y1, gx, tile_count);
 }
 
 // ---------------------------------------------------------------------------------------------
