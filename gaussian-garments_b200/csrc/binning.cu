@@ -148,7 +148,7 @@ __device__ void bitonic_sort_smem(uint64_t* a, uint32_t n) {
 __global__ void __launch_bounds__(SORT_THREADS)
 sort_pack_kernel(const uint32_t* __restrict__ tile_offset, uint64_t* __restrict__ keys,
                  const float2* __restrict__ xy, const float4* __restrict__ conic_o, const float* __restrict__ rgb,
-                 float4* __restrict__ p0, float4* __restrict__ p1, float4* __restrict__ p2, uint32_t capacity) {
+                 float4* __restrict__ p0, float4* __restrict__ p1, float4* __restrict__ p2, uint32_t capacity, int gx) {
     __shared__ uint64_t skeys[SORT_SMEM_KEYS];
     const uint32_t t = blockIdx.x;
     const uint32_t off = tile_offset[t];
@@ -165,6 +165,7 @@ sort_pack_kernel(const uint32_t* __restrict__ tile_offset, uint64_t* __restrict_
         bitonic_sort_block(keys + off, n);
         sorted = keys + off;
     }
+    const float tile_x = (float)((t % (uint32_t)gx) * TILE), tile_y = (float)((t / (uint32_t)gx) * TILE);
     for (uint32_t j = threadIdx.x; j < n; j += SORT_THREADS) {
         const uint64_t key = sorted[j];
         const uint32_t id = (uint32_t)(key & 0xffffffffu);
@@ -172,9 +173,29 @@ sort_pack_kernel(const uint32_t* __restrict__ tile_offset, uint64_t* __restrict_
         const float2 m = xy[id];
         const float4 co = conic_o[id];
         const float r = rgb[3 * (size_t)id], g = rgb[3 * (size_t)id + 1], b = rgb[3 * (size_t)id + 2];
+        // warp-overlap mask from the alpha >= 1/255 ellipse's bounding box (covariance = conic^-1)
+        uint32_t wmask = 0;
+        {
+            const float dc = co.x * co.z - co.y * co.y;
+            float ex, ey;
+            if (dc > 0.f && alpha_extent(co.w, co.z / dc, co.x / dc, ex, ey)) {
+                const float lx0 = m.x - ex - tile_x, lx1 = m.x + ex - tile_x;     // bbox in tile-local pixels
+                const float ly0 = m.y - ey - tile_y, ly1 = m.y + ey - tile_y;
+                const uint32_t xb = ((lx0 <= 7.f && lx1 >= 0.f) ? 1u : 0u) | ((lx0 <= 15.f && lx1 >= 8.f) ? 2u : 0u);
+                uint32_t yb = 0;
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (ly0 <= (float)(4 * q + 3) && ly1 >= (float)(4 * q)) yb |= 1u << q;
+#pragma unroll
+                for (int w = 0; w < 8; w++)
+                    if (((xb >> (w & 1)) & 1u) && ((yb >> (w >> 1)) & 1u)) wmask |= 1u << w;
+            } else if (!(dc > 0.f)) {
+                wmask = 0xffu;   // degenerate conic: no culling information
+            }
+        }
         p0[off + j] = make_float4(m.x, m.y, (-0.5f * LOG2E) * co.x, -LOG2E * co.y);
-        p1[off + j] = make_float4((-0.5f * LOG2E) * co.z, co.w, depth, __uint_as_float(id));
-        p2[off + j] = make_float4(r, g, b, 0.f);
+        p1[off + j] = make_float4((-0.5f * LOG2E) * co.z, co.w, depth, __uint_as_float(wmask));
+        p2[off + j] = make_float4(r, g, b, __uint_as_float(id));
     }
 }
 
@@ -192,7 +213,7 @@ int launch_sort_pack(const gg_view& v, const GeomWS& g, const TileWS& t, uint64_
     const int gx = (v.image_width + TILE - 1) / TILE, gy = (v.image_height + TILE - 1) / TILE;
     const int T = gx * gy;
     if (T == 0 || v.num_gaussians == 0) return 0;
-    sort_pack_kernel<<<T, SORT_THREADS, 0, s>>>(t.offset, keys, g.xy, g.conic_o, g.rgb, r.p0, r.p1, r.p2, capacity);
+    sort_pack_kernel<<<T, SORT_THREADS, 0, s>>>(t.offset, keys, g.xy, g.conic_o, g.rgb, r.p0, r.p1, r.p2, capacity, gx);
     return 1;
 }
 

@@ -13,7 +13,7 @@
 
 namespace gg {
 
-constexpr int BWD_BATCH = 64;
+constexpr int BWD_BATCH = 64;   // = 2 ballot words of the per-warp entry mask
 constexpr int BWD_STAGES = 2;
 constexpr int BWD_WARPS = TILE_PIX / 32;
 constexpr int ACC_STRIDE = 12;   // 10 used; keeps float4 alignment
@@ -131,7 +131,26 @@ blend_bwd_kernel(const uint32_t* __restrict__ tile_offset, const float4* __restr
         const int cnt = min(BWD_BATCH, (int)n - b * BWD_BATCH);
         mbar_wait(&full[st], (uint32_t)(q / BWD_STAGES) & 1u);
         const uint32_t r0 = smem_u32(&s0[st][0]), r1 = smem_u32(&s1[st][0]), r2 = smem_u32(&s2[st][0]);
-        for (int j = cnt - 1; j >= 0; j--) {
+        // entries this warp may touch: bit `warp` of the record's warp-overlap mask (two ballots per batch);
+        // entries whose alpha >= 1/255 bounding box misses this warp's 8x4 block cost nothing
+        uint32_t m_lo, m_hi;
+        {
+            const uint32_t w0 = (lane < cnt) ? __float_as_uint(lds32(r1 + 16u * lane + 12u)) : 0u;
+            const uint32_t w1 = (lane + 32 < cnt) ? __float_as_uint(lds32(r1 + 16u * (lane + 32) + 12u)) : 0u;
+            m_lo = __ballot_sync(0xffffffffu, (w0 >> warp) & 1u);
+            m_hi = __ballot_sync(0xffffffffu, (w1 >> warp) & 1u);
+        }
+        while (m_hi | m_lo) {
+            int j;
+            if (m_hi) {
+                const int bit = 31 - __clz(m_hi);
+                m_hi &= ~(1u << bit);
+                j = 32 + bit;
+            } else {
+                const int bit = 31 - __clz(m_lo);
+                m_lo &= ~(1u << bit);
+                j = bit;
+            }
             const uint32_t idx = (uint32_t)(b * BWD_BATCH + j);
             const float4 a = lds128(r0 + 16u * j);
             const float4 c = lds128(r1 + 16u * j);
@@ -180,7 +199,7 @@ blend_bwd_kernel(const uint32_t* __restrict__ tile_offset, const float4* __restr
         // fold the 8 warp slots; 3 work items (float4, float4, float2) per record
         for (int item = threadIdx.x; item < cnt * 3; item += TILE_PIX) {
             const int j = item / 3, part = item - j * 3;
-            const uint32_t id = __float_as_uint(s1[st][j].w);
+            const uint32_t id = __float_as_uint(s2[st][j].w);
             if (part < 2) {
                 float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll

