@@ -13,7 +13,7 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "libgg_raster.so")
+LIB_PATH = os.environ.get("GG_RASTER_LIB") or os.path.join(CSRC, "libgg_raster.so")   # override: dev experiments
 SOURCES = ["project.cu", "binning.cu", "blend_fwd.cu", "blend_bwd.cu", "preprocess_bwd.cu", "c_api.cu"]
 HEADERS = ["common.cuh", os.path.join("..", "..", "include", "gg_raster.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

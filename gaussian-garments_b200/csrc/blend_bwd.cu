@@ -52,7 +52,10 @@ __device__ __forceinline__ float warp_reduce_scatter10(const float* v, int lane,
     return u;
 }
 
-__global__ void __launch_bounds__(TILE_PIX)
+#ifndef GG_BWD_MINB
+#define GG_BWD_MINB 4
+#endif
+__global__ void __launch_bounds__(TILE_PIX, GG_BWD_MINB)
 blend_bwd_kernel(const uint32_t* __restrict__ tile_offset, const float4* __restrict__ p0,
                  const float4* __restrict__ p1, const float4* __restrict__ p2, int W, int H, int gx,
                  const float* __restrict__ bg, const uint32_t* __restrict__ n_contrib,

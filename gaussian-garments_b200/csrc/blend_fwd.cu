@@ -14,7 +14,10 @@ namespace gg {
 constexpr int FWD_BATCH = 128;
 constexpr int FWD_STAGES = 3;
 
-__global__ void __launch_bounds__(TILE_PIX)
+#ifndef GG_FWD_MINB
+#define GG_FWD_MINB 6
+#endif
+__global__ void __launch_bounds__(TILE_PIX, GG_FWD_MINB)
 blend_fwd_kernel(const uint32_t* __restrict__ tile_offset, const float4* __restrict__ p0,
                  const float4* __restrict__ p1, const float4* __restrict__ p2, uint32_t capacity, int W, int H, int gx,
                  const float* __restrict__ bg, float* __restrict__ out_color, float* __restrict__ out_depth,
