@@ -110,7 +110,7 @@ def load():
         lib.gg_backward_workspace_bytes.argtypes = [P(GGView), P(sz)]
         lib.gg_forward_project.argtypes = [P(GGView), P(GGInputs), vp, vp, vp, vp, i32, vp]
         lib.gg_forward_color.argtypes = [P(GGView), P(GGInputs), vp, vp, i32, vp]
-        lib.gg_forward_render.argtypes = [P(GGView), P(GGInputs), vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, i32, vp]
+        lib.gg_forward_render.argtypes = [P(GGView), P(GGInputs), vp, vp, vp, vp, i64, i64, vp, vp, vp, vp, vp, i32, vp]
         lib.gg_backward.argtypes = [P(GGView), P(GGInputs), vp, vp, i64, vp, vp, vp] + [vp] * 11 + [i32, vp]
         lib.gg_mark_visible.argtypes = [C.c_int32, vp, vp, vp, vp, i32, vp]
         lib.gg_debug_read_geom.argtypes = [P(GGView), vp, vp, vp, vp, vp, vp, i32, vp]

@@ -87,7 +87,8 @@ __device__ void bitonic_sort_block(Ptr a, uint32_t n) {
 }
 
 constexpr int SORT_THREADS = 256;
-constexpr uint32_t SORT_SMEM_KEYS = 4096;   // 32 KB of keys per CTA; larger tiles sort in L2/global
+constexpr uint32_t SORT_SMEM_KEYS = 4096;   // default: 32 KB of keys per CTA (7 CTAs/SM)
+constexpr uint32_t SORT_SMEM_KEYS_MAX = 24576;   // 192 KB dynamic variant for dense scenes; beyond: L2/global
 
 // Shared-memory variant with ~4x fewer CTA barriers: every step whose comparators stay inside an
 // aligned 64-key block (all of k <= 64, and the stride <= 32 tail of every later merge) is done by
@@ -148,15 +149,16 @@ __device__ void bitonic_sort_smem(uint64_t* a, uint32_t n) {
 __global__ void __launch_bounds__(SORT_THREADS)
 sort_pack_kernel(const uint32_t* __restrict__ tile_offset, uint64_t* __restrict__ keys,
                  const float2* __restrict__ xy, const float4* __restrict__ conic_o, const float* __restrict__ rgb,
-                 float4* __restrict__ p0, float4* __restrict__ p1, float4* __restrict__ p2, uint32_t capacity, int gx) {
-    __shared__ uint64_t skeys[SORT_SMEM_KEYS];
+                 float4* __restrict__ p0, float4* __restrict__ p1, float4* __restrict__ p2, uint32_t capacity, int gx,
+                 uint32_t smem_keys) {
+    extern __shared__ __align__(16) uint64_t skeys[];
     const uint32_t t = blockIdx.x;
     const uint32_t off = tile_offset[t];
     uint32_t n = tile_offset[t + 1] - off;
     if (n == 0) return;
     if (off + n > capacity) return;   // overflow is reported by the host wrapper (K > capacity)
     const uint64_t* sorted;
-    if (n <= SORT_SMEM_KEYS) {
+    if (n <= smem_keys) {
         for (uint32_t j = threadIdx.x; j < n; j += SORT_THREADS) skeys[j] = keys[off + j];
         __syncthreads();
         if (n > 1) bitonic_sort_smem(skeys, n);
@@ -167,35 +169,11 @@ sort_pack_kernel(const uint32_t* __restrict__ tile_offset, uint64_t* __restrict_
     }
     const float tile_x = (float)((t % (uint32_t)gx) * TILE), tile_y = (float)((t / (uint32_t)gx) * TILE);
     for (uint32_t j = threadIdx.x; j < n; j += SORT_THREADS) {
-        const uint64_t key = sorted[j];
-        const uint32_t id = (uint32_t)(key & 0xffffffffu);
-        const float depth = __uint_as_float((uint32_t)(key >> 32));
-        const float2 m = xy[id];
-        const float4 co = conic_o[id];
-        const float r = rgb[3 * (size_t)id], g = rgb[3 * (size_t)id + 1], b = rgb[3 * (size_t)id + 2];
-        // warp-overlap mask from the alpha >= 1/255 ellipse's bounding box (covariance = conic^-1)
-        uint32_t wmask = 0;
-        {
-            const float dc = co.x * co.z - co.y * co.y;
-            float ex, ey;
-            if (dc > 0.f && alpha_extent(co.w, co.z / dc, co.x / dc, ex, ey)) {
-                const float lx0 = m.x - ex - tile_x, lx1 = m.x + ex - tile_x;     // bbox in tile-local pixels
-                const float ly0 = m.y - ey - tile_y, ly1 = m.y + ey - tile_y;
-                const uint32_t xb = ((lx0 <= 7.f && lx1 >= 0.f) ? 1u : 0u) | ((lx0 <= 15.f && lx1 >= 8.f) ? 2u : 0u);
-                uint32_t yb = 0;
-#pragma unroll
-                for (int q = 0; q < 4; q++)
-                    if (ly0 <= (float)(4 * q + 3) && ly1 >= (float)(4 * q)) yb |= 1u << q;
-#pragma unroll
-                for (int w = 0; w < 8; w++)
-                    if (((xb >> (w & 1)) & 1u) && ((yb >> (w >> 1)) & 1u)) wmask |= 1u << w;
-            } else if (!(dc > 0.f)) {
-                wmask = 0xffu;   // degenerate conic: no culling information
-            }
-        }
-        p0[off + j] = make_float4(m.x, m.y, (-0.5f * LOG2E) * co.x, -LOG2E * co.y);
-        p1[off + j] = make_float4((-0.5f * LOG2E) * co.z, co.w, depth, __uint_as_float(wmask));
-        p2[off + j] = make_float4(r, g, b, __uint_as_float(id));
+        float4 q0, q1, q2;
+        pack_record(sorted[j], xy, conic_o, rgb, tile_x, tile_y, q0, q1, q2);
+        p0[off + j] = q0;
+        p1[off + j] = q1;
+        p2[off + j] = q2;
     }
 }
 
@@ -209,11 +187,207 @@ int launch_emit(const gg_view& v, const GeomWS& g, const TileWS& t, const int32_
 }
 
 int launch_sort_pack(const gg_view& v, const GeomWS& g, const TileWS& t, uint64_t* keys, const RecordWS& r,
-                     uint32_t capacity, cudaStream_t s) {
+                     uint32_t capacity, uint32_t max_tile_instances, cudaStream_t s) {
     const int gx = (v.image_width + TILE - 1) / TILE, gy = (v.image_height + TILE - 1) / TILE;
     const int T = gx * gy;
     if (T == 0 || v.num_gaussians == 0) return 0;
-    sort_pack_kernel<<<T, SORT_THREADS, 0, s>>>(t.offset, keys, g.xy, g.conic_o, g.rgb, r.p0, r.p1, r.p2, capacity, gx);
+    // shared-memory budget from the largest tile (0 = unknown -> largest variant): 32 KB keeps 7 CTAs/SM for
+    // ordinary scenes; dense scenes trade occupancy for an in-smem sort of up to 24576 keys per tile
+    uint32_t smem_keys = SORT_SMEM_KEYS;
+    if (max_tile_instances == 0 || max_tile_instances > SORT_SMEM_KEYS) {
+        smem_keys = 8192;
+        while (smem_keys < SORT_SMEM_KEYS_MAX && smem_keys < max_tile_instances) smem_keys += 8192;
+        if (max_tile_instances == 0) smem_keys = SORT_SMEM_KEYS_MAX;
+    }
+    const size_t bytes = (size_t)smem_keys * sizeof(uint64_t);
+    if (bytes > 48 * 1024)
+        cudaFuncSetAttribute(sort_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    sort_pack_kernel<<<T, SORT_THREADS, bytes, s>>>(t.offset, keys, g.xy, g.conic_o, g.rgb, r.p0, r.p1, r.p2, capacity,
+                                                     gx, smem_keys);
+    return 1;
+}
+
+// =============================================================================================
+// Lazy fused forward (dense scenes): per tile, bucket the keys by depth in O(n), then sort + pack +
+// blend ONE BUCKET AT A TIME and stop as soon as all 256 pixels are saturated.  In the 2M-Gaussian
+// 2160p stress config a tile's list holds ~7000 entries of which the blend consumes a few hundred:
+// sorting everything (sort_pack_kernel) cost 152 ms/view there, 95 % of the forward+backward time.
+// The order produced is identical to the full sort: buckets are a monotone function of depth and each
+// bucket is ordered by (depth bits, Gaussian index).  Only the consumed prefix of the packed records
+// is written; backward never reads past the tile's last contributor.
+// =============================================================================================
+constexpr uint32_t LZ_CAP = 2048;     // keys sorted in shared memory per run (16 KB)
+constexpr int LZ_CHUNK = 256;         // records staged per blend round (one gather per thread)
+constexpr uint32_t LZ_MAXB = 1024;    // depth buckets per tile at most
+
+__global__ void __launch_bounds__(TILE_PIX)
+blend_fwd_lazy_kernel(const uint32_t* __restrict__ tile_offset, const uint64_t* __restrict__ keys,
+                      uint64_t* __restrict__ keys2, const float2* __restrict__ xy,
+                      const float4* __restrict__ conic_o, const float* __restrict__ rgb, float4* __restrict__ p0,
+                      float4* __restrict__ p1, float4* __restrict__ p2, uint32_t capacity, int W, int H, int gx,
+                      const float* __restrict__ bg, float* __restrict__ out_color, float* __restrict__ out_depth,
+                      float* __restrict__ out_alpha, uint32_t* __restrict__ n_contrib, float* __restrict__ final_T) {
+    __shared__ __align__(16) uint64_t skeys[LZ_CAP];
+    __shared__ __align__(16) float4 c0[LZ_CHUNK];
+    __shared__ __align__(16) float4 c1[LZ_CHUNK];
+    __shared__ __align__(16) float4 c2[LZ_CHUNK];
+    __shared__ uint32_t boff[LZ_MAXB + 1];
+    __shared__ uint32_t cursor[LZ_MAXB];
+    __shared__ uint32_t red_min[8], red_max[8];
+
+    const uint32_t tile = blockIdx.x;
+    const int tx = tile % gx, ty = tile / gx;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int px = tx * TILE + (warp & 1) * 8 + (lane & 7);
+    const int py = ty * TILE + (warp >> 1) * 4 + (lane >> 3);
+    const bool inside = px < W && py < H;
+    const float fx = (float)px, fy = (float)py;
+    const float tile_x = (float)(tx * TILE), tile_y = (float)(ty * TILE);
+
+    const uint32_t off = tile_offset[tile];
+    uint32_t n = tile_offset[tile + 1] - off;
+    if (off + n > capacity) n = 0;
+
+    float T = 1.f, C0 = 0.f, C1 = 0.f, C2 = 0.f, Dp = 0.f, Ac = 0.f;
+    uint32_t last = 0, processed = 0;
+    bool done = !inside;
+    const uint32_t a0 = smem_u32(&c0[0]), a1 = smem_u32(&c1[0]), a2 = smem_u32(&c2[0]);
+
+    // consume a run of keys that is already in final order; returns true when the whole tile is saturated
+    auto process_run = [&](const uint64_t* run, uint32_t cnt) -> bool {
+        for (uint32_t c = 0; c < cnt; c += LZ_CHUNK) {
+            const uint32_t m = min((uint32_t)LZ_CHUNK, cnt - c);
+            if (threadIdx.x < m) {
+                float4 q0, q1, q2;
+                pack_record(run[c + threadIdx.x], xy, conic_o, rgb, tile_x, tile_y, q0, q1, q2);
+                c0[threadIdx.x] = q0; c1[threadIdx.x] = q1; c2[threadIdx.x] = q2;
+                const size_t dst = (size_t)off + processed + threadIdx.x;
+                p0[dst] = q0; p1[dst] = q1; p2[dst] = q2;
+            }
+            __syncthreads();
+            for (uint32_t j = 0; j < m; j++) {
+                if (__all_sync(0xffffffffu, done)) break;
+                const float4 cc = lds128(a1 + 16u * j);
+                if (!((__float_as_uint(cc.w) >> warp) & 1u)) continue;
+                const float4 a = lds128(a0 + 16u * j);
+                const float dx = a.x - fx, dy = a.y - fy;
+                const float e2 = dx * (a.z * dx + a.w * dy) + (cc.x * dy) * dy;
+                const float alpha = fminf(ALPHA_MAX, cc.y * ex2_approx(e2));
+                bool ok = !done && e2 <= 0.f && alpha >= ALPHA_MIN;
+                const float test_T = T * (1.f - alpha);
+                if (ok && test_T < T_STOP) {
+                    done = true;
+                    ok = false;
+                }
+                if (ok) {
+                    const float w = alpha * T;
+                    const float4 col = lds128(a2 + 16u * j);
+                    C0 += col.x * w; C1 += col.y * w; C2 += col.z * w;
+                    Dp += cc.z * w;
+                    Ac += w;
+                    T = test_T;
+                    last = processed + j + 1;
+                }
+            }
+            processed += m;
+            if (__syncthreads_count(done) == TILE_PIX) return true;
+        }
+        return false;
+    };
+
+    if (n > 0 && n <= LZ_CAP) {
+        for (uint32_t j = threadIdx.x; j < n; j += TILE_PIX) skeys[j] = keys[off + j];
+        __syncthreads();
+        if (n > 1) bitonic_sort_smem(skeys, n);
+        process_run(skeys, n);
+    } else if (n > LZ_CAP) {
+        // ---- pass A: depth range of the tile
+        uint32_t dmin = 0xffffffffu, dmax = 0u;
+        for (uint32_t j = threadIdx.x; j < n; j += TILE_PIX) {
+            const uint32_t d = (uint32_t)(keys[off + j] >> 32);
+            dmin = min(dmin, d);
+            dmax = max(dmax, d);
+        }
+        dmin = __reduce_min_sync(0xffffffffu, dmin);
+        dmax = __reduce_max_sync(0xffffffffu, dmax);
+        if (lane == 0) { red_min[warp] = dmin; red_max[warp] = dmax; }
+        const uint32_t NB = min(LZ_MAXB, (n + LZ_CAP / 2 - 1) / (LZ_CAP / 2));
+        for (uint32_t k = threadIdx.x; k <= NB; k += TILE_PIX) boff[k] = 0;
+        __syncthreads();
+#pragma unroll
+        for (int w = 0; w < 8; w++) { dmin = min(dmin, red_min[w]); dmax = max(dmax, red_max[w]); }
+        const float fmin_ = __uint_as_float(dmin), fmax_ = __uint_as_float(dmax);   // depths are positive floats
+        const float scale = (fmax_ > fmin_) ? (float)NB / (fmax_ - fmin_) : 0.f;
+        auto bucket_of = [&](uint64_t key) -> uint32_t {
+            const float d = __uint_as_float((uint32_t)(key >> 32));
+            return min(NB - 1u, (uint32_t)((d - fmin_) * scale));               // monotone in depth
+        };
+        // ---- pass B: histogram (shifted by one so the scan yields start offsets)
+        for (uint32_t j = threadIdx.x; j < n; j += TILE_PIX) atomicAdd(&boff[bucket_of(keys[off + j]) + 1], 1u);
+        __syncthreads();
+        if (warp == 0) {                                                        // inclusive scan of <= 1025 counters
+            uint32_t carry = 0;
+            for (uint32_t base = 0; base <= NB; base += 32) {
+                const uint32_t k = base + lane;
+                uint32_t v = (k <= NB) ? boff[k] : 0u;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xffffffffu, v, d);
+                    if (lane >= d) v += t;
+                }
+                v += carry;
+                if (k <= NB) boff[k] = v;
+                carry = __shfl_sync(0xffffffffu, v, 31);
+            }
+        }
+        __syncthreads();
+        for (uint32_t k = threadIdx.x; k < NB; k += TILE_PIX) cursor[k] = boff[k];
+        __syncthreads();
+        // ---- pass C: scatter into bucket order
+        for (uint32_t j = threadIdx.x; j < n; j += TILE_PIX) {
+            const uint64_t key = keys[off + j];
+            keys2[off + atomicAdd(&cursor[bucket_of(key)], 1u)] = key;
+        }
+        __syncthreads();
+        // ---- buckets front to back
+        for (uint32_t bk = 0; bk < NB; bk++) {
+            const uint32_t bo = boff[bk], cnt = boff[bk + 1] - bo;
+            if (cnt == 0) continue;
+            bool all_done;
+            if (cnt <= LZ_CAP) {
+                for (uint32_t j = threadIdx.x; j < cnt; j += TILE_PIX) skeys[j] = keys2[off + bo + j];
+                __syncthreads();
+                if (cnt > 1) bitonic_sort_smem(skeys, cnt);
+                all_done = process_run(skeys, cnt);
+            } else {                                     // degenerate depth distribution: sort this bucket in L2
+                bitonic_sort_block(keys2 + off + bo, cnt);
+                all_done = process_run(keys2 + off + bo, cnt);
+            }
+            if (all_done) break;
+        }
+    }
+
+    if (inside) {
+        const size_t P = (size_t)W * H, pid = (size_t)py * W + px;
+        out_color[pid] = C0 + T * bg[0];
+        out_color[P + pid] = C1 + T * bg[1];
+        out_color[2 * P + pid] = C2 + T * bg[2];
+        out_depth[pid] = Dp;
+        out_alpha[pid] = Ac;
+        n_contrib[pid] = last;
+        final_T[pid] = T;
+    }
+}
+
+int launch_blend_fwd_lazy(const gg_view& v, const gg_inputs& in, const GeomWS& g, const TileWS& t, uint64_t* keys,
+                          uint64_t* keys2, const RecordWS& r, const ImageWS& img, uint32_t capacity, float* out_color,
+                          float* out_depth, float* out_alpha, cudaStream_t s) {
+    const int gx = (v.image_width + TILE - 1) / TILE, gy = (v.image_height + TILE - 1) / TILE;
+    const int T = gx * gy;
+    if (T == 0) return 0;
+    blend_fwd_lazy_kernel<<<T, TILE_PIX, 0, s>>>(t.offset, keys, keys2, g.xy, g.conic_o, g.rgb, r.p0, r.p1, r.p2,
+                                                 capacity, v.image_width, v.image_height, gx, in.bg, out_color,
+                                                 out_depth, out_alpha, img.n_contrib, img.final_T);
     return 1;
 }
 

@@ -2,6 +2,7 @@
 // carving, launch sequencing, error reporting.  No allocation, no global mutable state.
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 #include <cstring>
 #include "common.cuh"
@@ -151,7 +152,8 @@ int gg_forward_workspace_bytes(const gg_view* view, size_t* geom_bytes, size_t* 
 
 int gg_instance_workspace_bytes(int64_t num_rendered, size_t* key_bytes, size_t* record_bytes) {
     if (num_rendered < 0 || num_rendered > 0xfffffff0ll) return fail(GG_E_BADARG, "num_rendered out of range");
-    if (key_bytes) *key_bytes = align_up((size_t)(num_rendered > 0 ? num_rendered : 1) * 8);
+    // two key arrays: tile-bucketed keys + the depth-bucketed copy of the lazy forward path
+    if (key_bytes) *key_bytes = 2 * align_up((size_t)(num_rendered > 0 ? num_rendered : 1) * 8);
     if (record_bytes) *record_bytes = record_layout(nullptr, num_rendered, nullptr);
     return 0;
 }
@@ -181,7 +183,7 @@ int gg_forward_project(const gg_view* view, const gg_inputs* in, void* geom_ws, 
     GG_AFTER("project_kernel");
     { ScopedKernelTimer kt(K_SCAN, s); g_launches += launch_tile_scan(T, t, s); }
     GG_AFTER("tile_scan_kernel");
-    if (num_rendered_host) GG_CUDA(cudaMemcpyAsync(num_rendered_host, t.misc, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    if (num_rendered_host) GG_CUDA(cudaMemcpyAsync(num_rendered_host, t.misc, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     return 0;
 }
 
@@ -201,8 +203,9 @@ int gg_forward_color(const gg_view* view, const gg_inputs* in, void* geom_ws, co
 }
 
 int gg_forward_render(const gg_view* view, const gg_inputs* in, const void* geom_ws, void* tile_ws, void* key_ws,
-                      void* record_ws, int64_t instance_capacity, void* image_ws, const int32_t* radii,
-                      float* out_color, float* out_depth, float* out_alpha, int device, void* stream) {
+                      void* record_ws, int64_t instance_capacity, int64_t max_tile_instances, void* image_ws,
+                      const int32_t* radii, float* out_color, float* out_depth, float* out_alpha, int device,
+                      void* stream) {
     if (int rc = check_view(view)) return rc;
     if (int rc = check_inputs(view, in)) return rc;
     if (!geom_ws || !tile_ws || !key_ws || !record_ws || !image_ws || !out_color || !out_depth || !out_alpha)
@@ -230,9 +233,24 @@ int gg_forward_render(const gg_view* view, const gg_inputs* in, const void* geom
     const uint32_t cap = (uint32_t)instance_capacity;
     { ScopedKernelTimer kt(K_EMIT, s); g_launches += launch_emit(*view, g, t, radii, (uint64_t*)key_ws, cap, s); }
     GG_AFTER("emit_kernel");
-    { ScopedKernelTimer kt(K_SORTPACK, s); g_launches += launch_sort_pack(*view, g, t, (uint64_t*)key_ws, r, cap, s); }
-    GG_AFTER("sort_pack_kernel");
-    { ScopedKernelTimer kt(K_BLENDFWD, s); g_launches += launch_blend_fwd(*view, *in, t, r, img, cap, out_color, out_depth, out_alpha, s); }
+    // Forward path: "tma" = per-tile full sort + pack, then the bulk-TMA streamed blend;
+    //               "lazy" = fused bucket-sort + pack + blend that stops at tile saturation (dense scenes).
+    // auto: lazy when some tile holds more instances than the default shared-memory sort handles.
+    bool lazy = max_tile_instances > 4096;
+    if (const char* e = getenv("GG_FWD_PATH")) {
+        if (!strcmp(e, "lazy")) lazy = true;
+        else if (!strcmp(e, "tma")) lazy = false;
+    }
+    if (lazy) {
+        uint64_t* keys2 = (uint64_t*)((char*)key_ws + align_up((size_t)(instance_capacity > 0 ? instance_capacity : 1) * 8));
+        ScopedKernelTimer kt(K_BLENDFWD, s);
+        g_launches += launch_blend_fwd_lazy(*view, *in, g, t, (uint64_t*)key_ws, keys2, r, img, cap, out_color,
+                                            out_depth, out_alpha, s);
+    } else {
+        { ScopedKernelTimer kt(K_SORTPACK, s); g_launches += launch_sort_pack(*view, g, t, (uint64_t*)key_ws, r, cap, (uint32_t)(max_tile_instances < 0 ? 0 : max_tile_instances), s); }
+        GG_AFTER("sort_pack_kernel");
+        { ScopedKernelTimer kt(K_BLENDFWD, s); g_launches += launch_blend_fwd(*view, *in, t, r, img, cap, out_color, out_depth, out_alpha, s); }
+    }
     GG_AFTER("blend_fwd_kernel");
     return 0;
 }

@@ -45,7 +45,7 @@ struct TileWS {
     uint32_t* count;   // [T]   instances per tile          (zeroed by stage 1)
     uint32_t* fill;    // [T]   emit cursor                 (zeroed by stage 1)
     uint32_t* offset;  // [T+1] exclusive scan of count     (kept for backward)
-    uint32_t* misc;    // [8]   misc[0] = K (num_rendered)
+    uint32_t* misc;    // [8]   misc[0] = K (num_rendered), misc[1] = largest per-tile count
 };
 inline size_t tile_layout(void* base, int64_t T, TileWS* ws) {
     char* p = (char*)base;
@@ -131,9 +131,12 @@ int launch_sh_color(const gg_view& v, const gg_inputs& in, const GeomWS& g, cons
 int launch_emit(const gg_view& v, const GeomWS& g, const TileWS& t, const int32_t* radii, uint64_t* keys,
                 uint32_t capacity, cudaStream_t s);
 int launch_sort_pack(const gg_view& v, const GeomWS& g, const TileWS& t, uint64_t* keys, const RecordWS& r,
-                     uint32_t capacity, cudaStream_t s);
+                     uint32_t capacity, uint32_t max_tile_instances, cudaStream_t s);
 int launch_blend_fwd(const gg_view& v, const gg_inputs& in, const TileWS& t, const RecordWS& r, const ImageWS& img,
                      uint32_t capacity, float* out_color, float* out_depth, float* out_alpha, cudaStream_t s);
+int launch_blend_fwd_lazy(const gg_view& v, const gg_inputs& in, const GeomWS& g, const TileWS& t, uint64_t* keys,
+                          uint64_t* keys2, const RecordWS& r, const ImageWS& img, uint32_t capacity, float* out_color,
+                          float* out_depth, float* out_alpha, cudaStream_t s);
 int launch_blend_bwd(const gg_view& v, const gg_inputs& in, const TileWS& t, const RecordWS& r, const ImageWS& img,
                      const float* dL_dcolor, const float* dL_ddepth, const float* dL_dalpha, const AccumWS& acc,
                      cudaStream_t s);
@@ -299,6 +302,41 @@ __device__ __forceinline__ bool alpha_extent(float opacity, float cov_xx, float 
     ex = sqrtf(two_tau * cov_xx) * 1.001f + 0.02f;
     ey = sqrtf(two_tau * cov_yy) * 1.001f + 0.02f;
     return true;
+}
+
+// Build the three packed planes of one (tile, Gaussian) instance from its sort key and the projected
+// per-Gaussian records (shared by sort_pack_kernel and the lazy fused forward).
+__device__ __forceinline__ void pack_record(uint64_t key, const float2* __restrict__ xy,
+                                            const float4* __restrict__ conic_o, const float* __restrict__ rgb,
+                                            float tile_x, float tile_y, float4& q0, float4& q1, float4& q2) {
+    const uint32_t id = (uint32_t)(key & 0xffffffffu);
+    const float depth = __uint_as_float((uint32_t)(key >> 32));
+    const float2 m = xy[id];
+    const float4 co = conic_o[id];
+    const float r = rgb[3 * (size_t)id], g = rgb[3 * (size_t)id + 1], b = rgb[3 * (size_t)id + 2];
+    // warp-overlap mask from the alpha >= 1/255 ellipse's bounding box (covariance = conic^-1)
+    uint32_t wmask = 0;
+    const float dc = co.x * co.z - co.y * co.y;
+    float ex, ey;
+    if (dc > 0.f) {
+        if (alpha_extent(co.w, co.z / dc, co.x / dc, ex, ey)) {
+            const float lx0 = m.x - ex - tile_x, lx1 = m.x + ex - tile_x;     // bbox in tile-local pixels
+            const float ly0 = m.y - ey - tile_y, ly1 = m.y + ey - tile_y;
+            const uint32_t xb = ((lx0 <= 7.f && lx1 >= 0.f) ? 1u : 0u) | ((lx0 <= 15.f && lx1 >= 8.f) ? 2u : 0u);
+            uint32_t yb = 0;
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                if (ly0 <= (float)(4 * q + 3) && ly1 >= (float)(4 * q)) yb |= 1u << q;
+#pragma unroll
+            for (int w = 0; w < 8; w++)
+                if (((xb >> (w & 1)) & 1u) && ((yb >> (w >> 1)) & 1u)) wmask |= 1u << w;
+        }
+    } else {
+        wmask = 0xffu;   // degenerate conic: no culling information
+    }
+    q0 = make_float4(m.x, m.y, (-0.5f * LOG2E) * co.x, -LOG2E * co.y);
+    q1 = make_float4((-0.5f * LOG2E) * co.z, co.w, depth, __uint_as_float(wmask));
+    q2 = make_float4(r, g, b, __uint_as_float(id));
 }
 
 // Shared EWA projection state of one Gaussian (used by project and by preprocess backward)

@@ -130,8 +130,15 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(int T, const uint32_t* 
     const int tid = threadIdx.x;
     const int per = (T + 1023) / 1024;
     const int beg = min(tid * per, T), end = min(beg + per, T);
-    uint32_t local = 0;
-    for (int i = beg; i < end; i++) local += count[i];
+    uint32_t local = 0, lmax = 0;
+    for (int i = beg; i < end; i++) {
+        const uint32_t c = count[i];
+        local += c;
+        lmax = max(lmax, c);
+    }
+    lmax = __reduce_max_sync(0xffffffffu, lmax);
+    __shared__ uint32_t warp_max[32];
+    if ((tid & 31) == 0) warp_max[tid >> 5] = lmax;
     // inclusive warp scan
     uint32_t v = local;
     const int lane = tid & 31, wid = tid >> 5;
@@ -159,7 +166,10 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(int T, const uint32_t* 
     }
     if (tid == 1023) {
         offset[T] = warp_tot[31];
-        misc[0] = warp_tot[31];
+        misc[0] = warp_tot[31];                     // K = num_rendered
+        uint32_t mx = 0;
+        for (int w = 0; w < 32; w++) mx = max(mx, warp_max[w]);
+        misc[1] = mx;                               // largest per-tile instance count (picks the sort variant)
     }
 }
 

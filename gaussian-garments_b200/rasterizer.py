@@ -68,7 +68,7 @@ def _pinned_word(device_index: int) -> torch.Tensor:
         cache = _tls.words = {}
     w = cache.get(device_index)
     if w is None:
-        w = cache[device_index] = torch.zeros(1, dtype=torch.int32).pin_memory()
+        w = cache[device_index] = torch.zeros(2, dtype=torch.int32).pin_memory()
     return w
 
 
@@ -149,7 +149,7 @@ class _RasterizeGaussians(torch.autograd.Function):
                 _capi.check(lib.gg_forward_workspace_bytes(C.byref(view), C.byref(gb), C.byref(tb), C.byref(ib)),
                             "gg_forward_workspace_bytes")
                 geom_ws, tile_ws, image_ws = _ws(gb.value, dev), _ws(tb.value, dev), _ws(ib.value, dev)
-                K = 0
+                K, max_tile = 0, 0
                 if N > 0:
                     word = _pinned_word(di)
                     _capi.check(lib.gg_forward_project(C.byref(view), C.byref(inputs), geom_ws.data_ptr(),
@@ -160,12 +160,13 @@ class _RasterizeGaussians(torch.autograd.Function):
                     _capi.check(lib.gg_forward_color(C.byref(view), C.byref(inputs), geom_ws.data_ptr(),
                                                      radii.data_ptr(), di, sp), "gg_forward_color")
                     k_ready.synchronize()        # only the scan + 4-byte copy; the SH kernel keeps running
-                    K = int(word.item()) & 0xFFFFFFFF
+                    K, max_tile = (int(v) & 0xFFFFFFFF for v in word.tolist())
                 kb, rb = C.c_size_t(), C.c_size_t()
                 _capi.check(lib.gg_instance_workspace_bytes(K, C.byref(kb), C.byref(rb)), "gg_instance_workspace_bytes")
                 key_ws, record_ws = _ws(kb.value, dev), _ws(rb.value, dev)
                 _capi.check(lib.gg_forward_render(C.byref(view), C.byref(inputs), geom_ws.data_ptr(), tile_ws.data_ptr(),
-                                                  key_ws.data_ptr(), record_ws.data_ptr(), K, image_ws.data_ptr(),
+                                                  key_ws.data_ptr(), record_ws.data_ptr(), K, max_tile,
+                                                  image_ws.data_ptr(),
                                                   _ptr(radii), color.data_ptr(), depth.data_ptr(), alpha.data_ptr(),
                                                   di, sp), "gg_forward_render")
         except Exception:

@@ -46,35 +46,19 @@ def face_orientation(verts: torch.Tensor, faces: torch.Tensor):
 
 
 def rotmat_to_unitquat_xyzw(R: torch.Tensor) -> torch.Tensor:
-    """Rotation matrix -> unit quaternion (x,y,z,w); largest-component branch selection."""
+    """Rotation matrix -> unit quaternion (x,y,z,w); largest-component branch selection (same algorithm as
+    roma.rotmat_to_unitquat, written with torch.where so that it never synchronises with the host)."""
     m00, m01, m02 = R[:, 0, 0], R[:, 0, 1], R[:, 0, 2]
     m10, m11, m12 = R[:, 1, 0], R[:, 1, 1], R[:, 1, 2]
     m20, m21, m22 = R[:, 2, 0], R[:, 2, 1], R[:, 2, 2]
     tr = m00 + m11 + m22
-    dec = torch.stack([m00, m11, m22, tr], dim=1)
-    choice = dec.argmax(dim=1)
-    q = torch.zeros(R.shape[0], 4, dtype=R.dtype, device=R.device)
-    # choice == 3 : trace largest
-    c = choice == 3
-    q[c, 0] = (m21 - m12)[c]
-    q[c, 1] = (m02 - m20)[c]
-    q[c, 2] = (m10 - m01)[c]
-    q[c, 3] = (1 + tr)[c]
-    c = choice == 0
-    q[c, 0] = (1 - tr + 2 * m00)[c]
-    q[c, 1] = (m10 + m01)[c]
-    q[c, 2] = (m20 + m02)[c]
-    q[c, 3] = (m21 - m12)[c]
-    c = choice == 1
-    q[c, 0] = (m10 + m01)[c]
-    q[c, 1] = (1 - tr + 2 * m11)[c]
-    q[c, 2] = (m21 + m12)[c]
-    q[c, 3] = (m02 - m20)[c]
-    c = choice == 2
-    q[c, 0] = (m20 + m02)[c]
-    q[c, 1] = (m21 + m12)[c]
-    q[c, 2] = (1 - tr + 2 * m22)[c]
-    q[c, 3] = (m10 - m01)[c]
+    choice = torch.stack([m00, m11, m22, tr], dim=1).argmax(dim=1)
+    q3 = torch.stack([m21 - m12, m02 - m20, m10 - m01, 1 + tr], dim=1)                 # trace largest
+    q0 = torch.stack([1 - tr + 2 * m00, m10 + m01, m20 + m02, m21 - m12], dim=1)
+    q1 = torch.stack([m10 + m01, 1 - tr + 2 * m11, m21 + m12, m02 - m20], dim=1)
+    q2 = torch.stack([m20 + m02, m21 + m12, 1 - tr + 2 * m22, m10 - m01], dim=1)
+    c = choice[:, None]
+    q = torch.where(c == 3, q3, torch.where(c == 0, q0, torch.where(c == 1, q1, q2)))
     return q / q.norm(dim=1, keepdim=True)
 
 

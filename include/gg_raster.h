@@ -86,8 +86,9 @@ int gg_backward_workspace_bytes(const gg_view* view, size_t* accum_bytes);
  * (geometry part of preprocessCUDA + InclusiveSum + the num_rendered read-back).
  * Launches: project (3D->2D covariance, cull, tile rectangle, per-tile counts) and the tile
  * scan.  Writes radii[N] (int32, an output tensor of the call).  `num_rendered_host` may be
- * NULL or a pinned host word that receives K through an async copy enqueued on `stream`
- * right after the scan: record an event after this call and wait on it before reading.    */
+ * NULL or TWO pinned host words that receive {K, largest per-tile instance count} through an
+ * async copy enqueued on `stream` right after the scan: record an event after this call and
+ * wait on it before reading.                                                              */
 int gg_forward_project(const gg_view* view, const gg_inputs* in, void* geom_ws, void* tile_ws,
                        int32_t* radii, uint32_t* num_rendered_host, int device, void* stream);
 
@@ -100,12 +101,13 @@ int gg_forward_color(const gg_view* view, const gg_inputs* in, void* geom_ws, co
 /* ---- forward, stage 2: replaces the second half of `_C.rasterize_gaussians`
  * (duplicateWithKeys + RadixSort + identifyTileRanges + renderCUDA).
  * Launches: instance emit, per-tile depth sort + record packing, front-to-back blend.
- * `instance_capacity` is the K the key/record workspaces were sized for.
- * Outputs: out_color[3,H,W], out_depth[1,H,W], out_alpha[1,H,W].                          */
+ * `instance_capacity` is the K the key/record workspaces were sized for;
+ * `max_tile_instances` (second word from gg_forward_project; 0 = unknown) sizes the per-tile
+ * sort's shared memory.  Outputs: out_color[3,H,W], out_depth[1,H,W], out_alpha[1,H,W].   */
 int gg_forward_render(const gg_view* view, const gg_inputs* in, const void* geom_ws, void* tile_ws,
-                      void* key_ws, void* record_ws, int64_t instance_capacity, void* image_ws,
-                      const int32_t* radii, float* out_color, float* out_depth, float* out_alpha,
-                      int device, void* stream);
+                      void* key_ws, void* record_ws, int64_t instance_capacity,
+                      int64_t max_tile_instances, void* image_ws, const int32_t* radii,
+                      float* out_color, float* out_depth, float* out_alpha, int device, void* stream);
 
 /* ---- backward: replaces `_C.rasterize_gaussians_backward`
  * (renderCUDA bwd + computeCov2DCUDA + preprocessCUDA bwd).

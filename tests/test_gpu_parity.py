@@ -377,3 +377,61 @@ def test_stage1_geometry_is_bit_identical_to_oracle():
     assert int(area(u)) <= int(area(o))
     assert float((rgb.cpu()[vis] - g["rgb"][vis]).abs().max()) < 2e-6      # SH sum order differs: continuous only
     del keep
+
+
+# ------------------------------------------------------------------------------------ lazy fused forward path
+@pytest.fixture
+def lazy_path(monkeypatch):
+    monkeypatch.setenv("GG_FWD_PATH", "lazy")
+    yield
+    monkeypatch.delenv("GG_FWD_PATH", raising=False)
+
+
+def test_lazy_forward_path_matches_oracle_cfg1(lazy_path):
+    st = gg.scenes.random_cloud(10_000)
+    cam = gg.scenes.cfg1_camera()
+    S = h.settings_for(cam, st, device=torch.device("cuda:0"))
+    grads = _upstream_grads(cam.image_height, cam.image_width)
+    got = h.run_cuda(S, st, grads)
+    ref = h.run_c_oracle(S, st, grads)
+    h.assert_images_close(got, ref)
+    h.assert_grads_close(got["grads"], ref["grads"])
+
+
+def _dense_tile_state(n, same_depth=False, opacity=0.02, seed=5):
+    st = gg.scenes.random_cloud(n, seed=13)
+    g = torch.Generator().manual_seed(seed)
+    z = torch.zeros(n, 1) if same_depth else torch.rand(n, 1, generator=g) * 2
+    st.means3D = torch.cat([torch.randn(n, 2, generator=g) * 0.01, z], dim=1)      # camera T=(0,0,4): depth 4..6
+    st.scales = torch.full((n, 3), 0.004)
+    st.opacities = torch.full((n, 1), opacity)
+    return st
+
+
+@pytest.mark.parametrize("same_depth", [False, True])
+def test_lazy_forward_path_bucketed_tiles(lazy_path, same_depth):
+    """> 2048 instances per tile: depth-bucketed lazy sort; all-equal depths force the degenerate (L2 sort) branch."""
+    st = _dense_tile_state(6000, same_depth=same_depth)
+    cam = gg.scenes.cfg1_camera(64, 64)
+    S = h.settings_for(cam, st, device=torch.device("cuda:0"))
+    grads = _upstream_grads(64, 64)
+    got = h.run_cuda(S, st, grads)
+    ref = h.run_c_oracle(S, st, grads)
+    h.assert_images_close(got, ref, max_fragile_frac=0.05)
+    h.assert_grads_close(got["grads"], ref["grads"], tol=3e-3)
+
+
+def test_lazy_path_equals_tma_path_when_tiles_saturate(monkeypatch):
+    """Opaque dense tile: the lazy path stops after the first buckets; result must equal the full-sort path."""
+    st = _dense_tile_state(9000, opacity=0.6)
+    cam = gg.scenes.cfg1_camera(64, 64)
+    S = h.settings_for(cam, st, device=torch.device("cuda:0"))
+    grads = _upstream_grads(64, 64)
+    monkeypatch.setenv("GG_FWD_PATH", "tma")
+    a = h.run_cuda(S, st, grads)
+    monkeypatch.setenv("GG_FWD_PATH", "lazy")
+    b = h.run_cuda(S, st, grads)
+    monkeypatch.delenv("GG_FWD_PATH")
+    assert torch.equal(a["color"], b["color"]) and torch.equal(a["alpha"], b["alpha"]) and torch.equal(a["depth"], b["depth"])
+    for k in ("means3D", "shs", "opacities", "scales", "rotations"):
+        assert h.rel_inf(a["grads"][k], b["grads"][k]) < 1e-4
