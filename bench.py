@@ -107,7 +107,7 @@ def algorithmic_bytes(N, K, P, T, M=16):
         "sh_color": (12 + 12 * M) * N + 12 * N,
         "emit": 20 * N + 8 * K,
         "sort_pack": 8 * K + 36 * K + 48 * K,                   # keys in, gathered geom, packed planes out
-        "blend_fwd": 48 * K + 28 * P,
+        "blend_fwd": 48 * K + 28 * P,                           # (lazy path: + the sort_pack row, fused)
         "blend_bwd": 48 * K + 28 * P + 40 * N,
         "preprocess_bwd": (40 + 44 + 12 * M) * N + (56 + 12 * M) * N,
     }
@@ -305,15 +305,21 @@ def main():
     K = int(sum(Ks) / len(Ks))
     gx, gy = (W + 15) // 16, (H + 15) // 16
     ab = algorithmic_bytes(args.gaussians, K, W * H, gx * gy)
+    traffic = {}
+    try:   # per-launch dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture (profiles/)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))
+        traffic = {k: int(v["traffic"]) for k, v in tj["kernels"].items()}
+    except Exception:
+        pass
     kernels = []
     for name, ms in sorted(acc.items(), key=lambda kv: -kv[1]):
         gbs = ab[name] / (ms * 1e-3) / 1e9
         kernels.append({"kernel": name, "ms": round(ms, 4), "alg_bytes": int(ab[name]), "achieved_gbs": round(gbs, 1),
-                        "frac": round(gbs / peak_gbs, 4)})
+                        "frac": round(gbs / peak_gbs, 4), "traffic": traffic.get(name)})
     dom = kernels[0]
     interactions = 256 * K
     roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_gbs"], "peak": peak_gbs, "unit": "GB/s",
-                "frac": dom["frac"], "traffic": None, "peak_source": peak_src, "avg_launch_ms": dom["ms"],
+                "frac": dom["frac"], "traffic": dom["traffic"], "peak_source": peak_src, "avg_launch_ms": dom["ms"],
                 "num_rendered": K, "pixel_gaussian_pairs": interactions,
                 "note": "blend kernels are FP32/SFU/issue bound by construction (256*K pixel-Gaussian pairs); "
                         "streaming kernels carry the HBM claim -- see `kernels`",
