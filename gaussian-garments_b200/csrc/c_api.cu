@@ -14,9 +14,10 @@ thread_local char g_err[512] = "";
 // worker thread: launch counts and per-kernel events must be visible from the caller's thread.
 std::atomic<int64_t> g_launches{0};
 
-enum KernelSlot { K_PROJECT = 0, K_SCAN, K_SHCOLOR, K_EMIT, K_SORTPACK, K_BLENDFWD, K_BLENDBWD, K_PREBWD, K_COUNT };
+enum KernelSlot { K_PROJECT = 0, K_SCAN, K_SHCOLOR, K_EMIT, K_SORTPACK, K_BLENDFWD, K_BLENDBWD, K_PREBWD, K_MESHFWD, K_MESHBWD, K_COUNT };
 const char* const kKernelNames[K_COUNT] = {"project", "tile_scan", "sh_color", "emit", "sort_pack",
-                                           "blend_fwd", "blend_bwd", "preprocess_bwd"};
+                                           "blend_fwd", "blend_bwd", "preprocess_bwd", "mesh_bind_fwd",
+                                           "mesh_bind_bwd"};
 std::atomic<int> g_timing{0};
 std::mutex g_timing_mu;
 cudaEvent_t g_ev[K_COUNT][2];
@@ -322,6 +323,67 @@ int gg_debug_read_geom(const gg_view* view, const void* geom_ws, float* xy, floa
     if (rect) {   // unpack on the host side is not possible for device destinations: copy packed pairs
         GG_CUDA(cudaMemcpyAsync(rect, g.rect, N * 8, k, s));
     }
+    return 0;
+}
+
+// ---- fused mesh-binding transform ------------------------------------------
+int gg_mesh_bind_workspace_bytes(int32_t num_faces, size_t* frame_bytes) {
+    if (num_faces < 0) return fail(GG_E_BADARG, "negative num_faces");
+    if (frame_bytes) *frame_bytes = align_up((size_t)(num_faces > 0 ? num_faces : 1) * 17 * sizeof(float));
+    return 0;
+}
+
+int gg_mesh_bind_forward(int32_t num_vertices, int32_t num_faces, int32_t num_gaussians, const float* verts,
+                         const int32_t* faces, const int32_t* binding, const float* local_xyz,
+                         const float* local_log_scaling, const float* local_rotation, void* frame_ws, float* out_xyz,
+                         float* out_scaling, float* out_rotation, int device, void* stream) {
+    (void)num_vertices;
+    if (num_faces < 0 || num_gaussians < 0) return fail(GG_E_BADARG, "negative size");
+    if (num_gaussians > 0 && (!verts || !faces || !binding || !local_xyz || !local_log_scaling || !local_rotation ||
+                              !frame_ws || !out_xyz || !out_scaling || !out_rotation))
+        return fail(GG_E_BADARG, "NULL argument");
+    if (!aligned16(local_rotation) || !aligned16(out_rotation)) return fail(GG_E_ALIGN, "rotation tensors not 16-byte aligned");
+    GG_CUDA(cudaSetDevice(device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const gg_view* view = nullptr;
+    {
+        ScopedKernelTimer kt(K_MESHFWD, s);
+        g_launches += launch_mesh_bind_forward(num_faces, num_gaussians, verts, faces, binding, local_xyz, local_log_scaling,
+                                               local_rotation, (float*)frame_ws, out_xyz, out_scaling, out_rotation, s);
+    }
+    GG_AFTER("mesh_bind_forward");
+    return 0;
+}
+
+int gg_mesh_bind_backward(int32_t num_vertices, int32_t num_faces, int32_t num_gaussians, const float* verts,
+                          const int32_t* faces, const int32_t* binding, const float* local_xyz,
+                          const float* local_log_scaling, const float* local_rotation, const void* frame_ws,
+                          void* frame_grad_ws, const float* dL_dxyz, const float* dL_dscaling, const float* dL_drotation,
+                          float* dL_dverts, float* dL_dlocal_xyz, float* dL_dlocal_log_scaling, float* dL_dlocal_rotation,
+                          int device, void* stream) {
+    if (num_vertices < 0 || num_faces < 0 || num_gaussians < 0) return fail(GG_E_BADARG, "negative size");
+    if (num_gaussians == 0) return 0;
+    if (!verts || !faces || !binding || !local_xyz || !local_log_scaling || !local_rotation || !frame_ws)
+        return fail(GG_E_BADARG, "NULL argument");
+    if (dL_dverts && !frame_grad_ws) return fail(GG_E_BADARG, "frame_grad_ws is required for dL_dverts");
+    if (!aligned16(local_rotation) || (dL_drotation && !aligned16(dL_drotation)) ||
+        (dL_dlocal_rotation && !aligned16(dL_dlocal_rotation)))
+        return fail(GG_E_ALIGN, "rotation tensors not 16-byte aligned");
+    GG_CUDA(cudaSetDevice(device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const gg_view* view = nullptr;
+    if (dL_dverts) {
+        GG_CUDA(cudaMemsetAsync(frame_grad_ws, 0, (size_t)num_faces * 17 * sizeof(float), s));
+        GG_CUDA(cudaMemsetAsync(dL_dverts, 0, (size_t)num_vertices * 3 * sizeof(float), s));
+    }
+    {
+        ScopedKernelTimer kt(K_MESHBWD, s);
+        g_launches += launch_mesh_bind_backward(num_faces, num_gaussians, verts, faces, binding, local_xyz, local_log_scaling,
+                                                local_rotation, (const float*)frame_ws, dL_dxyz, dL_dscaling, dL_drotation,
+                                                (float*)frame_grad_ws, dL_dverts, dL_dlocal_xyz, dL_dlocal_log_scaling,
+                                                dL_dlocal_rotation, s);
+    }
+    GG_AFTER("mesh_bind_backward");
     return 0;
 }
 

@@ -145,6 +145,13 @@ int launch_preprocess_bwd(const gg_view& v, const gg_inputs& in, const int32_t* 
                           float* dL_dopacities, float* dL_dscales, float* dL_drotations, float* dL_dcov3D,
                           cudaStream_t s);
 int launch_mark_visible(int N, const float* means3D, const float* viewmatrix, uint8_t* visible, cudaStream_t s);
+int launch_mesh_bind_forward(int F, int N, const float* verts, const int32_t* faces, const int32_t* binding,
+                             const float* lxyz, const float* lscal, const float* lrot, float* frames, float* o_xyz,
+                             float* o_scal, float* o_rot, cudaStream_t s);
+int launch_mesh_bind_backward(int F, int N, const float* verts, const int32_t* faces, const int32_t* binding,
+                              const float* lxyz, const float* lscal, const float* lrot, const float* frames,
+                              const float* g_xyz, const float* g_scal, const float* g_rot, float* gF, float* g_verts,
+                              float* gl_xyz, float* gl_scal, float* gl_rot, cudaStream_t s);
 
 #ifdef __CUDACC__
 // ---------------------------------------------------------------------------------------------

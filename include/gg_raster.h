@@ -129,6 +129,27 @@ int gg_backward(const gg_view* view, const gg_inputs* in, const void* tile_ws, c
 int gg_mark_visible(int32_t num_gaussians, const float* means3D, const float* viewmatrix,
                     const float* projmatrix, uint8_t* visible, int device, void* stream);
 
+/* ---- fused mesh-binding transform ("next" row N1) ------------------------------------------
+ * Replaces the torch op chain of /root/reference/scene/mesh_gaussian_model.py:90-128
+ * (update_face_coor, get_xyz, get_scaling, get_rotation) and utils/graphics_utils.py:118-137
+ * (compute_face_orientation): per-face frames from verts[V,3] / faces[F,3] (int32), then per
+ * Gaussian (binding[N] int32 = its face):  xyz = R_f local_xyz * s_f + c_f,
+ * scaling = exp(local_log_scaling) * s_f,  rotation = normalize(q_f (x) normalize(local_rotation)) (wxyz).
+ * frame_ws (gg_mesh_bind_workspace_bytes) is written by forward and read by backward;
+ * frame_grad_ws has the same size.  Backward outputs may be NULL (not wanted); dL_dverts is
+ * zero-filled and accumulated here (this is the gradient stage 2 all-reduces).              */
+int gg_mesh_bind_workspace_bytes(int32_t num_faces, size_t* frame_bytes);
+int gg_mesh_bind_forward(int32_t num_vertices, int32_t num_faces, int32_t num_gaussians, const float* verts,
+                         const int32_t* faces, const int32_t* binding, const float* local_xyz,
+                         const float* local_log_scaling, const float* local_rotation, void* frame_ws,
+                         float* out_xyz, float* out_scaling, float* out_rotation, int device, void* stream);
+int gg_mesh_bind_backward(int32_t num_vertices, int32_t num_faces, int32_t num_gaussians, const float* verts,
+                          const int32_t* faces, const int32_t* binding, const float* local_xyz,
+                          const float* local_log_scaling, const float* local_rotation, const void* frame_ws,
+                          void* frame_grad_ws, const float* dL_dxyz, const float* dL_dscaling,
+                          const float* dL_drotation, float* dL_dverts, float* dL_dlocal_xyz,
+                          float* dL_dlocal_log_scaling, float* dL_dlocal_rotation, int device, void* stream);
+
 /* ---- introspection ------------------------------------------------------------------------ */
 /* copies stage-1 per-Gaussian records out of geom_ws for stage-wise parity tests
  * (xy[N,2], depth[N], conic_opacity[N,4], rgb[N,3], rect[N,2] uint32 packed as

@@ -435,3 +435,65 @@ def test_lazy_path_equals_tma_path_when_tiles_saturate(monkeypatch):
     assert torch.equal(a["color"], b["color"]) and torch.equal(a["alpha"], b["alpha"]) and torch.equal(a["depth"], b["depth"])
     for k in ("means3D", "shs", "opacities", "scales", "rotations"):
         assert h.rel_inf(a["grads"][k], b["grads"][k]) < 1e-4
+
+
+# ------------------------------------------------------------------------------------ N1: fused mesh binding
+def test_fused_mesh_binding_matches_torch_chain():
+    """gg_mesh_bind_forward/backward vs autograd through the restated reference chain
+    (scene/mesh_gaussian_model.py:90-128), incl. gradients to mesh.v."""
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(11)
+    m = gg.scenes.MeshBoundGaussians(n_faces_around=40, n_along=12, per_face=6, seed=5)
+    m.mesh_v = m.mesh_v + 0.005 * torch.randn(m.mesh_v.shape, generator=g)
+    m._rotation = torch.randn(m._rotation.shape, generator=g)
+    m.to(dev)
+    N = m.binding.shape[0]
+    G = [torch.randn(N, 3, generator=g).to(dev), torch.randn(N, 3, generator=g).to(dev), torch.randn(N, 4, generator=g).to(dev)]
+
+    def leaves():
+        return [getattr(m, k).detach().clone().requires_grad_(True) for k in ("mesh_v", "_xyz", "_scaling", "_rotation")]
+
+    a = leaves()
+    xyz, sc, ro = gg.bind_to_mesh(a[0], m.mesh_f, m.binding, a[1], a[2], a[3])
+    ((xyz * G[0]).sum() + (sc * G[1]).sum() + (ro * G[2]).sum()).backward()
+
+    b = [t.double() for t in leaves()]
+    b = [t.detach().requires_grad_(True) for t in b]
+    ref = gg.scenes.MeshBoundGaussians.__new__(gg.scenes.MeshBoundGaussians)
+    ref.mesh_f, ref.binding = m.mesh_f, m.binding
+    ref.mesh_v, ref._xyz, ref._scaling, ref._rotation = b
+    ref.update_face_coor()
+    ((ref.get_xyz * G[0].double()).sum() + (ref.get_scaling * G[1].double()).sum() + (ref.get_rotation * G[2].double()).sum()).backward()
+
+    assert torch.allclose(xyz, ref.get_xyz.float(), atol=2e-6)
+    assert torch.allclose(sc, ref.get_scaling.float(), atol=1e-7, rtol=1e-5)
+    assert torch.allclose(ro, ref.get_rotation.float(), atol=2e-6)
+    for name, x, y in zip(("mesh_v", "_xyz", "_scaling", "_rotation"), a, b):
+        assert h.rel_inf(x.grad, y.grad.float()) < 1e-3, name
+
+
+def test_fused_mesh_binding_feeds_the_rasterizer():
+    """End to end: mesh.v gradient of a render through fused binding == through the torch chain."""
+    dev = torch.device("cuda:0")
+    m = gg.scenes.MeshBoundGaussians(n_faces_around=60, n_along=20, per_face=6, sh_degree=0, max_sh_degree=0, seed=9).to(dev)
+    cam = gg.scenes.ring_cameras(4, width=320, height=240)[1].to(dev)
+    S = h.dgr.GaussianRasterizationSettings(image_height=240, image_width=320, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy,
+                                            bg=m.bg, scale_modifier=1.0, viewmatrix=cam.world_view_transform,
+                                            projmatrix=cam.full_proj_transform, sh_degree=0, campos=cam.camera_center,
+                                            prefiltered=False, debug=False)
+    gt = torch.rand(3, 240, 320, device=dev)
+    grads = []
+    for fused in (False, True):
+        m.mesh_v = m.mesh_v.detach().clone().requires_grad_(True)
+        if fused:
+            xyz, sc, ro = gg.FusedMeshBinding(m).world()
+        else:
+            m.update_face_coor()
+            xyz, sc, ro = m.get_xyz, m.get_scaling, m.get_rotation
+        color, *_ = h.dgr.GaussianRasterizer(raster_settings=S)(
+            means3D=xyz, means2D=torch.zeros_like(xyz), shs=m.get_features, colors_precomp=None, opacities=m.get_opacity,
+            scales=sc, rotations=ro, cov3D_precomp=None)
+        (color - gt).abs().mean().backward()
+        grads.append(m.mesh_v.grad.clone())
+    assert float(grads[0].abs().max()) > 0
+    assert h.rel_inf(grads[1], grads[0]) < 2e-3

@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--gaussians", type=int, default=0)
+    ap.add_argument("--fused-binding", action="store_true", help="cfg4: fused mesh-binding kernels instead of the torch chain")
     args = ap.parse_args()
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
     torch.cuda.set_device(local)
@@ -59,7 +60,12 @@ def main():
             cams.append((c if i % 2 == 0 else gg.scenes.ring_cameras(32, width=1920, height=1080)[i]).to(dev))
         n_views = args.views or 32
 
+        fused = gg.FusedMeshBinding(model) if args.fused_binding else None
+
         def state_fn():
+            if fused is not None:
+                xyz, sc, ro = fused.world()
+                return (xyz, sc, ro, model.get_opacity, model.get_features)
             model.update_face_coor()
             return (model.get_xyz, model.get_scaling, model.get_rotation, model.get_opacity, model.get_features)
         sh_degree, bg = 0, model.bg
@@ -139,6 +145,7 @@ def main():
                                  "blend_bwd_ms": round(split.get("blend_bwd", 0), 4),
                                  "sort_share": round((split.get("sort_pack", 0) + split.get("emit", 0)) / max(tot, 1e-9), 3)},
                "grad_allreduce": "mesh.v only" if args.config == "cfg4" else "5 Gaussian tensors (flat bucket)",
+               "mesh_binding": ("fused kernels" if args.fused_binding else "torch chain") if args.config == "cfg4" else None,
                "mem_gb": round(torch.cuda.max_memory_allocated() / 1e9, 2)}
         print(json.dumps(out), flush=True)
     if world > 1:
