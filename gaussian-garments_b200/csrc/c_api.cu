@@ -14,10 +14,10 @@ thread_local char g_err[512] = "";
 // worker thread: launch counts and per-kernel events must be visible from the caller's thread.
 std::atomic<int64_t> g_launches{0};
 
-enum KernelSlot { K_PROJECT = 0, K_SCAN, K_SHCOLOR, K_EMIT, K_SORTPACK, K_BLENDFWD, K_BLENDBWD, K_PREBWD, K_MESHFWD, K_MESHBWD, K_COUNT };
+enum KernelSlot { K_PROJECT = 0, K_SCAN, K_SHCOLOR, K_EMIT, K_SORTPACK, K_BLENDFWD, K_BLENDBWD, K_PREBWD, K_MESHFWD, K_MESHBWD, K_LOSSFWD, K_LOSSBWD, K_COUNT };
 const char* const kKernelNames[K_COUNT] = {"project", "tile_scan", "sh_color", "emit", "sort_pack",
                                            "blend_fwd", "blend_bwd", "preprocess_bwd", "mesh_bind_fwd",
-                                           "mesh_bind_bwd"};
+                                           "mesh_bind_bwd", "photometric_fwd", "photometric_bwd"};
 std::atomic<int> g_timing{0};
 std::mutex g_timing_mu;
 cudaEvent_t g_ev[K_COUNT][2];
@@ -384,6 +384,61 @@ int gg_mesh_bind_backward(int32_t num_vertices, int32_t num_faces, int32_t num_g
                                                 dL_dlocal_rotation, s);
     }
     GG_AFTER("mesh_bind_backward");
+    return 0;
+}
+
+// ---- fused photometric loss --------------------------------------------------
+int gg_photometric_workspace_bytes(int32_t width, int32_t height, size_t* map_bytes) {
+    if (width < 0 || height < 0) return fail(GG_E_BADARG, "negative size");
+    // two double accumulators + three partial-derivative maps [3,H,W] (the maps are untouched when with_ssim = 0)
+    if (map_bytes) *map_bytes = 3 * align_up((size_t)3 * width * height * sizeof(float)) + 256;
+    return 0;
+}
+
+static void photometric_carve(void* ws, int W, int H, float** m1, float** m2, float** m3, double** sums) {
+    const size_t plane = align_up((size_t)3 * W * H * sizeof(float));
+    char* b = (char*)ws;
+    *sums = (double*)b;
+    *m1 = (float*)(b + 256);
+    *m2 = (float*)(b + 256 + plane);
+    *m3 = (float*)(b + 256 + 2 * plane);
+}
+
+int gg_photometric_forward(int32_t width, int32_t height, const float* image, const float* gt, const float* mask,
+                           void* map_ws, int32_t with_ssim, int device, void* stream) {
+    if (width <= 0 || height <= 0 || !image || !gt || !map_ws) return fail(GG_E_BADARG, "bad size or NULL argument");
+    GG_CUDA(cudaSetDevice(device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const gg_view* view = nullptr;
+    float *m1, *m2, *m3;
+    double* sums;
+    photometric_carve(map_ws, width, height, &m1, &m2, &m3, &sums);
+    GG_CUDA(cudaMemsetAsync(sums, 0, 2 * sizeof(double), s));
+    {
+        ScopedKernelTimer kt(K_LOSSFWD, s);
+        if (!with_ssim) m1 = m2 = m3 = nullptr;      // L1 only: no partial-derivative maps
+        g_launches += launch_photometric_fwd(width, height, image, gt, mask, m1, m2, m3, sums, s);
+    }
+    GG_AFTER("photometric_fwd_kernel");
+    return 0;
+}
+
+int gg_photometric_backward(int32_t width, int32_t height, const float* image, const float* gt, const float* mask,
+                            const void* map_ws, float coeff_l1, float coeff_ssim, const float* upstream_scalar,
+                            float* dL_dimage, int device, void* stream) {
+    if (width <= 0 || height <= 0 || !image || !gt || !map_ws || !dL_dimage) return fail(GG_E_BADARG, "bad size or NULL argument");
+    GG_CUDA(cudaSetDevice(device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const gg_view* view = nullptr;
+    float *m1, *m2, *m3;
+    double* sums;
+    photometric_carve(const_cast<void*>(map_ws), width, height, &m1, &m2, &m3, &sums);
+    if (coeff_ssim == 0.f) m1 = m2 = m3 = nullptr;       // forward was L1 only
+    {
+        ScopedKernelTimer kt(K_LOSSBWD, s);
+        g_launches += launch_photometric_bwd(width, height, image, gt, mask, m1, m2, m3, coeff_l1, coeff_ssim, upstream_scalar, dL_dimage, s);
+    }
+    GG_AFTER("photometric_bwd_kernel");
     return 0;
 }
 

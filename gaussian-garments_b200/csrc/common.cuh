@@ -145,6 +145,11 @@ int launch_preprocess_bwd(const gg_view& v, const gg_inputs& in, const int32_t* 
                           float* dL_dopacities, float* dL_dscales, float* dL_drotations, float* dL_dcov3D,
                           cudaStream_t s);
 int launch_mark_visible(int N, const float* means3D, const float* viewmatrix, uint8_t* visible, cudaStream_t s);
+int launch_photometric_fwd(int W, int H, const float* img, const float* gt, const float* mask, float* m1, float* m2,
+                           float* m3, double* sums, cudaStream_t s);
+int launch_photometric_bwd(int W, int H, const float* img, const float* gt, const float* mask, const float* m1,
+                           const float* m2, const float* m3, float c_l1, float c_ss, const float* g_scalar, float* g_img,
+                           cudaStream_t s);
 int launch_mesh_bind_forward(int F, int N, const float* verts, const int32_t* faces, const int32_t* binding,
                              const float* lxyz, const float* lscal, const float* lrot, float* frames, float* o_xyz,
                              float* o_scal, float* o_rot, cudaStream_t s);

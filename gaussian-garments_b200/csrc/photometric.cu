@@ -1,0 +1,188 @@
+// photometric.cu -- fused photometric loss ("next" row N2 of SURVEY.md 8f): masked L1 + SSIM(11x11 Gaussian
+// window, sigma 1.5) forward and backward in two kernels.
+//
+// Replaces, per iteration of the reference (s2_registration.py:259-260, s3_appearance.py:132-133),
+//   l1_loss(image, gt, mask)                /root/reference/utils/loss_utils.py:17-21
+//   ssim(image, gt, mask)                   /root/reference/utils/loss_utils.py:36-69
+// i.e. 5 depthwise 11x11 convolutions over 3xHxW forward (+ their autograd backward) and ~10 elementwise passes.
+// Here the window is applied separably out of shared memory: the forward kernel produces the two sums (L1, SSIM)
+// and the three per-pixel partial-derivative maps of the SSIM index; the backward kernel convolves those maps once
+// and emits dL/dimage directly (the L1 subgradient is fused in).  Zero padding, as conv2d(padding=5).
+#include "common.cuh"
+
+namespace gg {
+
+// gaussian(11, 1.5) of utils/loss_utils.py:26-28, float32 as the reference builds it
+__constant__ float kWin[11] = {1.028380124e-03f, 7.598758209e-03f, 3.600077331e-02f, 1.093606874e-01f,
+                               2.130055279e-01f, 2.660117149e-01f, 2.130055279e-01f, 1.093606874e-01f,
+                               3.600077331e-02f, 7.598758209e-03f, 1.028380124e-03f};
+constexpr int PT = 16;          // output tile edge
+constexpr int PH = 5;           // halo
+constexpr int PI = PT + 2 * PH; // 26
+constexpr float SSIM_C1 = 0.01f * 0.01f, SSIM_C2 = 0.03f * 0.03f;
+
+__device__ __forceinline__ float block_sum_256(float v, float* red) {
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    float t = (threadIdx.x < 8) ? red[threadIdx.x] : 0.f;
+    if (w == 0) t = warp_sum(t);
+    __syncthreads();
+    return t;     // valid in warp 0
+}
+
+// grid (ceil(W/16), ceil(H/16), 3 channels), block 256
+__global__ void __launch_bounds__(256)
+photometric_fwd_kernel(int W, int H, const float* __restrict__ img, const float* __restrict__ gt,
+                       const float* __restrict__ mask, float* __restrict__ m1, float* __restrict__ m2,
+                       float* __restrict__ m3, double* __restrict__ sums /*[2]: l1, ssim*/) {
+    __shared__ float sx[PI][PI + 1], sy[PI][PI + 1];
+    __shared__ float hz[5][PI][PT + 1];
+    __shared__ float red[8];
+    const int ch = blockIdx.z;
+    const int ox = blockIdx.x * PT, oy = blockIdx.y * PT;
+    const size_t plane = (size_t)W * H;
+    const float* I = img + ch * plane;
+    const float* G = gt + ch * plane;
+    for (int k = threadIdx.x; k < PI * PI; k += 256) {
+        const int ly = k / PI, lx = k - ly * PI;
+        const int gx_ = ox + lx - PH, gy_ = oy + ly - PH;
+        float x = 0.f, y = 0.f;
+        if (gx_ >= 0 && gx_ < W && gy_ >= 0 && gy_ < H) {
+            const size_t p = (size_t)gy_ * W + gx_;
+            const float mk = mask ? mask[p] : 1.f;
+            x = I[p] * mk;
+            y = G[p] * mk;
+        }
+        sx[ly][lx] = x;
+        sy[ly][lx] = y;
+    }
+    __syncthreads();
+    const bool with_ssim = m1 != nullptr;                       // block-uniform: lambda_dssim == 0 skips the SSIM work
+    if (with_ssim)
+    for (int k = threadIdx.x; k < PI * PT; k += 256) {        // horizontal pass
+        const int ly = k / PT, lx = k - ly * PT;
+        float a = 0.f, b = 0.f, c = 0.f, d = 0.f, e = 0.f;
+#pragma unroll
+        for (int t = 0; t < 11; t++) {
+            const float w = kWin[t], x = sx[ly][lx + t], y = sy[ly][lx + t];
+            a += w * x; b += w * y; c += w * x * x; d += w * y * y; e += w * x * y;
+        }
+        hz[0][ly][lx] = a; hz[1][ly][lx] = b; hz[2][ly][lx] = c; hz[3][ly][lx] = d; hz[4][ly][lx] = e;
+    }
+    __syncthreads();
+    const int lx = threadIdx.x & 15, ly = threadIdx.x >> 4;
+    const int px = ox + lx, py = oy + ly;
+    float l1 = 0.f, ss = 0.f;
+    if (px < W && py < H && !with_ssim) l1 = fabsf(sx[ly + PH][lx + PH] - sy[ly + PH][lx + PH]);
+    if (px < W && py < H && with_ssim) {
+        float mu1 = 0.f, mu2 = 0.f, exx = 0.f, eyy = 0.f, exy = 0.f;
+#pragma unroll
+        for (int t = 0; t < 11; t++) {
+            const float w = kWin[t];
+            mu1 += w * hz[0][ly + t][lx]; mu2 += w * hz[1][ly + t][lx]; exx += w * hz[2][ly + t][lx];
+            eyy += w * hz[3][ly + t][lx]; exy += w * hz[4][ly + t][lx];
+        }
+        const float mu1s = mu1 * mu1, mu2s = mu2 * mu2, mu12 = mu1 * mu2;
+        const float s1 = exx - mu1s, s2 = eyy - mu2s, s12 = exy - mu12;
+        const float A = mu1s + mu2s + SSIM_C1, B = s1 + s2 + SSIM_C2, Cc = 2.f * mu12 + SSIM_C1, D = 2.f * s12 + SSIM_C2;
+        const float iAB = 1.f / (A * B);
+        ss = Cc * D * iAB;
+        const size_t p = (size_t)py * W + px + ch * plane;
+        // d ssim / d(mu1, E[x^2], E[xy]) with y fixed
+        m1[p] = ((2.f * mu2 * D - 2.f * mu2 * Cc) * A * B - Cc * D * (2.f * mu1 * B - 2.f * mu1 * A)) * iAB * iAB;
+        m2[p] = -Cc * D * iAB / B;
+        m3[p] = 2.f * Cc * iAB;
+        l1 = fabsf(sx[ly + PH][lx + PH] - sy[ly + PH][lx + PH]);     // |(img - gt) * mask|
+    }
+    const float tl1 = block_sum_256(l1, red);
+    const float tss = block_sum_256(ss, red);
+    if (threadIdx.x == 0) {
+        atomicAdd(&sums[0], (double)tl1);
+        atomicAdd(&sums[1], (double)tss);
+    }
+}
+
+// dL/dimage = mask * [ c_l1 * sign((img-gt)*mask) + c_ss * (conv(m1) + 2 x conv(m2) + y conv(m3)) ]
+__global__ void __launch_bounds__(256)
+photometric_bwd_kernel(int W, int H, const float* __restrict__ img, const float* __restrict__ gt,
+                       const float* __restrict__ mask, const float* __restrict__ m1, const float* __restrict__ m2,
+                       const float* __restrict__ m3, float c_l1, float c_ss, const float* __restrict__ g_scalar,
+                       float* __restrict__ g_img) {
+    __shared__ float s[3][PI][PI + 1];
+    if (g_scalar) {           // upstream dL/dloss stays on the device: no host round trip
+        const float g = g_scalar[0];
+        c_l1 *= g;
+        c_ss *= g;
+    }
+    __shared__ float hz[3][PI][PT + 1];
+    const int ch = blockIdx.z;
+    const int ox = blockIdx.x * PT, oy = blockIdx.y * PT;
+    const size_t plane = (size_t)W * H;
+    if (m1 == nullptr) {                                        // L1 only
+        const int lx = threadIdx.x & 15, ly = threadIdx.x >> 4;
+        const int px = ox + lx, py = oy + ly;
+        if (px >= W || py >= H) return;
+        const size_t pp = (size_t)py * W + px, p = pp + ch * plane;
+        const float mk = mask ? mask[pp] : 1.f;
+        const float d = (img[p] - gt[p]) * mk;
+        g_img[p] = mk * c_l1 * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f));
+        return;
+    }
+    for (int k = threadIdx.x; k < PI * PI; k += 256) {
+        const int ly = k / PI, lx = k - ly * PI;
+        const int gx_ = ox + lx - PH, gy_ = oy + ly - PH;
+        float a = 0.f, b = 0.f, c = 0.f;
+        if (gx_ >= 0 && gx_ < W && gy_ >= 0 && gy_ < H) {
+            const size_t p = (size_t)gy_ * W + gx_ + ch * plane;
+            a = m1[p]; b = m2[p]; c = m3[p];
+        }
+        s[0][ly][lx] = a; s[1][ly][lx] = b; s[2][ly][lx] = c;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < PI * PT; k += 256) {
+        const int ly = k / PT, lx = k - ly * PT;
+        float a = 0.f, b = 0.f, c = 0.f;
+#pragma unroll
+        for (int t = 0; t < 11; t++) {
+            const float w = kWin[t];
+            a += w * s[0][ly][lx + t]; b += w * s[1][ly][lx + t]; c += w * s[2][ly][lx + t];
+        }
+        hz[0][ly][lx] = a; hz[1][ly][lx] = b; hz[2][ly][lx] = c;
+    }
+    __syncthreads();
+    const int lx = threadIdx.x & 15, ly = threadIdx.x >> 4;
+    const int px = ox + lx, py = oy + ly;
+    if (px >= W || py >= H) return;
+    float a = 0.f, b = 0.f, c = 0.f;
+#pragma unroll
+    for (int t = 0; t < 11; t++) {
+        const float w = kWin[t];
+        a += w * hz[0][ly + t][lx]; b += w * hz[1][ly + t][lx]; c += w * hz[2][ly + t][lx];
+    }
+    const size_t pp = (size_t)py * W + px, p = pp + ch * plane;
+    const float mk = mask ? mask[pp] : 1.f;
+    const float x = img[p] * mk, y = gt[p] * mk;
+    const float d = x - y;
+    const float sgn = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+    g_img[p] = mk * (c_l1 * sgn + c_ss * (a + 2.f * x * b + y * c));
+}
+
+int launch_photometric_fwd(int W, int H, const float* img, const float* gt, const float* mask, float* m1, float* m2,
+                           float* m3, double* sums, cudaStream_t s) {
+    if (W <= 0 || H <= 0) return 0;
+    dim3 grid((W + PT - 1) / PT, (H + PT - 1) / PT, 3);
+    photometric_fwd_kernel<<<grid, 256, 0, s>>>(W, H, img, gt, mask, m1, m2, m3, sums);
+    return 1;
+}
+int launch_photometric_bwd(int W, int H, const float* img, const float* gt, const float* mask, const float* m1,
+                           const float* m2, const float* m3, float c_l1, float c_ss, const float* g_scalar, float* g_img,
+                           cudaStream_t s) {
+    if (W <= 0 || H <= 0) return 0;
+    dim3 grid((W + PT - 1) / PT, (H + PT - 1) / PT, 3);
+    photometric_bwd_kernel<<<grid, 256, 0, s>>>(W, H, img, gt, mask, m1, m2, m3, c_l1, c_ss, g_scalar, g_img);
+    return 1;
+}
+
+}  // namespace gg

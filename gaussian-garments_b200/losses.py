@@ -1,0 +1,84 @@
+"""Fused photometric loss ("next" row N2 of SURVEY.md 8f) -- host side.
+
+Mirrors the two calls the reference makes right after `render()`
+(/root/reference/s2_registration.py:259-260, s3_appearance.py:132-133):
+
+    loss_dict['img']  = l1_loss(image, gt_image, mask) * (1.0 - lambda_dssim)       utils/loss_utils.py:17-21
+    loss_dict['ssim'] = 1.0 - ssim(image, gt_image, mask) * lambda_dssim            utils/loss_utils.py:36-69
+
+    total, l1, ssim_value = photometric_loss(image, gt_image, mask, lambda_dssim)   # total == img + ssim terms
+
+The arithmetic is csrc/photometric.cu behind gg_photometric_forward / gg_photometric_backward.  Unlike the
+reference's ssim(), the rendered image and the ground truth are NOT multiplied by the mask in place.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _capi
+
+
+def _prep(t, name):
+    if not t.is_cuda:
+        raise RuntimeError(f"gaussian-garments_b200: `{name}` must be a CUDA tensor (there is no CPU path)")
+    t = t.float() if t.dtype != torch.float32 else t
+    return t.contiguous()
+
+
+class _Photometric(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, image, gt, mask, lambda_dssim: float):
+        lib = _capi.load()
+        img, g = _prep(image, "image"), _prep(gt, "gt")
+        if img.dim() != 3 or img.shape[0] != 3 or g.shape != img.shape:
+            raise RuntimeError("photometric_loss expects image and gt of shape [3,H,W]")
+        m = None if mask is None else _prep(mask, "mask").reshape(-1)
+        H, W = int(img.shape[1]), int(img.shape[2])
+        if m is not None and m.numel() != H * W:
+            raise RuntimeError("mask must have H*W elements ([1,H,W])")
+        dev = img.device
+        di = dev.index if dev.index is not None else torch.cuda.current_device()
+        wb = C.c_size_t()
+        _capi.check(lib.gg_photometric_workspace_bytes(W, H, C.byref(wb)), "gg_photometric_workspace_bytes")
+        ws = torch.empty(wb.value if lambda_dssim != 0.0 else 256, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            sp = torch.cuda.current_stream(dev).cuda_stream
+            _capi.check(lib.gg_photometric_forward(W, H, img.data_ptr(), g.data_ptr(), None if m is None else m.data_ptr(),
+                                                   ws.data_ptr(), 1 if lambda_dssim != 0.0 else 0, di, sp), "gg_photometric_forward")
+        sums = ws[:16].view(torch.float64)
+        n = 3.0 * H * W
+        l1 = (sums[0] / n).float()
+        ssim_v = (sums[1] / n).float()
+        total = l1 * (1.0 - lambda_dssim) + (1.0 - ssim_v * lambda_dssim)
+        ctx.save_for_backward(img, g, m if m is not None else torch.empty(0, device=dev), ws)
+        ctx.lam, ctx.hw = float(lambda_dssim), (H, W)
+        ctx.mark_non_differentiable(l1, ssim_v)
+        return total, l1, ssim_v
+
+    @staticmethod
+    def backward(ctx, g_total, _g_l1, _g_ssim):
+        lib = _capi.load()
+        img, g, m, ws = ctx.saved_tensors
+        H, W = ctx.hw
+        dev = img.device
+        di = dev.index if dev.index is not None else torch.cuda.current_device()
+        n = 3.0 * H * W
+        gs = g_total.reshape(1).float().contiguous()
+        out = torch.empty_like(img)
+        with torch.cuda.device(dev):
+            sp = torch.cuda.current_stream(dev).cuda_stream
+            _capi.check(lib.gg_photometric_backward(W, H, img.data_ptr(), g.data_ptr(), m.data_ptr() if m.numel() else None,
+                                                    ws.data_ptr(), (1.0 - ctx.lam) / n, -ctx.lam / n, gs.data_ptr(),
+                                                    out.data_ptr(), di, sp), "gg_photometric_backward")
+        return out, None, None, None
+
+
+def photometric_loss(image: torch.Tensor, gt: torch.Tensor, mask: Optional[torch.Tensor] = None,
+                     lambda_dssim: float = 0.2):
+    """-> (total, l1, ssim): total = l1*(1-lambda) + 1 - ssim*lambda is differentiable w.r.t. `image`;
+    l1 and ssim are the detached components (the values of the reference's l1_loss / ssim)."""
+    return _Photometric.apply(image, gt, mask, float(lambda_dssim))

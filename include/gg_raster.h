@@ -150,6 +150,22 @@ int gg_mesh_bind_backward(int32_t num_vertices, int32_t num_faces, int32_t num_g
                           const float* dL_drotation, float* dL_dverts, float* dL_dlocal_xyz,
                           float* dL_dlocal_log_scaling, float* dL_dlocal_rotation, int device, void* stream);
 
+/* ---- fused photometric loss ("next" row N2) -------------------------------------------------
+ * Replaces l1_loss(image, gt, mask) and ssim(image, gt, mask) of /root/reference/utils/loss_utils.py:17-69
+ * as used at s2_registration.py:259-260 / s3_appearance.py:132-133.  image, gt: [3,H,W]; mask: [1,H,W]
+ * or NULL.  Forward writes into map_ws: two double sums at offset 0 {sum |(image-gt)*mask|, sum of the SSIM
+ * map} followed by the three partial-derivative maps the backward consumes.  l1_loss = sums[0]/(3HW),
+ * ssim = sums[1]/(3HW); with_ssim = 0 (lambda_dssim == 0) skips the SSIM work, then coeff_ssim must be 0.
+ * Backward: dL_dimage = coeff_l1 * d(sum|.|)/dimage + coeff_ssim * d(sum ssim)/dimage
+ * (the caller folds 1/(3HW) and lambda_dssim into the two coefficients; `upstream_scalar`, a DEVICE float
+ * or NULL, multiplies both -- the loss gradient never visits the host).                                  */
+int gg_photometric_workspace_bytes(int32_t width, int32_t height, size_t* map_bytes);
+int gg_photometric_forward(int32_t width, int32_t height, const float* image, const float* gt, const float* mask,
+                           void* map_ws, int32_t with_ssim, int device, void* stream);
+int gg_photometric_backward(int32_t width, int32_t height, const float* image, const float* gt, const float* mask,
+                            const void* map_ws, float coeff_l1, float coeff_ssim, const float* upstream_scalar,
+                            float* dL_dimage, int device, void* stream);
+
 /* ---- introspection ------------------------------------------------------------------------ */
 /* copies stage-1 per-Gaussian records out of geom_ws for stage-wise parity tests
  * (xy[N,2], depth[N], conic_opacity[N,4], rgb[N,3], rect[N,2] uint32 packed as

@@ -104,7 +104,26 @@ def main():
         for name, v in c.items():
             flat[f"cam{k}_{name}"] = np.asarray(v)
     np.savez(os.path.join(OUT, "camera.npz"), n_cams=len(cams), **flat)
-    print("wrote sh.npz cov3d.npz camera.npz to", OUT)
+    # ---- photometric loss (utils/loss_utils.py); the reference's ssim() mutates its inputs in place -> clones
+    from utils import loss_utils
+    gl = torch.Generator().manual_seed(99)
+    out = {}
+    for tag, (h, w, use_mask) in {"a": (40, 52, False), "b": (37, 45, True)}.items():
+        img = torch.rand(3, h, w, generator=gl)
+        gt = (img + 0.2 * torch.randn(3, h, w, generator=gl)).clamp(0, 1)
+        mask = (torch.rand(1, h, w, generator=gl) > 0.3).float() if use_mask else None
+        x = img.clone().requires_grad_(True)
+        l1 = loss_utils.l1_loss(x, gt, mask)
+        xs = x * 1.0                                      # non-leaf copy: ssim() multiplies it by the mask in place
+        ss = loss_utils.ssim(xs, gt.clone(), mask.clone() if mask is not None else None)
+        total = l1 * (1.0 - 0.2) + (1.0 - ss * 0.2)       # s2_registration.py:259-260 with lambda_dssim = 0.2
+        total.backward()
+        out.update({f"{tag}_img": img.numpy(), f"{tag}_gt": gt.numpy(), f"{tag}_l1": l1.item(), f"{tag}_ssim": ss.item(),
+                    f"{tag}_total": total.item(), f"{tag}_grad": x.grad.numpy()})
+        if mask is not None:
+            out[f"{tag}_mask"] = mask.numpy()
+    np.savez(os.path.join(OUT, "loss.npz"), **out)
+    print("wrote sh.npz cov3d.npz camera.npz loss.npz to", OUT)
 
 
 if __name__ == "__main__":

@@ -497,3 +497,40 @@ def test_fused_mesh_binding_feeds_the_rasterizer():
         grads.append(m.mesh_v.grad.clone())
     assert float(grads[0].abs().max()) > 0
     assert h.rel_inf(grads[1], grads[0]) < 2e-3
+
+
+# ------------------------------------------------------------------------------------ N2: fused photometric loss
+@pytest.mark.parametrize("shape,use_mask", [((3, 37, 45), True), ((3, 40, 52), False), ((3, 270, 480), True)])
+def test_fused_photometric_loss_matches_oracle(shape, use_mask):
+    from oracle import loss_oracle as lo
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(4)
+    img = torch.rand(*shape, generator=g)
+    gt = (img + 0.2 * torch.randn(*shape, generator=g)).clamp(0, 1)
+    mask = (torch.rand(1, *shape[1:], generator=g) > 0.3).float() if use_mask else None
+    x = img.to(dev).requires_grad_(True)
+    total, l1, ss = gg.photometric_loss(x, gt.to(dev), None if mask is None else mask.to(dev), 0.2)
+    (total * 1.7).backward()                       # non-trivial upstream scalar stays on the device
+    xr = img.double().requires_grad_(True)
+    ref_total = lo.total_loss(xr, gt.double(), None if mask is None else mask.double(), 0.2)
+    (ref_total * 1.7).backward()
+    assert abs(float(l1) - float(lo.l1_loss(img.double(), gt.double(), None if mask is None else mask.double()))) < 1e-6
+    assert abs(float(ss) - float(lo.ssim(img.double(), gt.double(), None if mask is None else mask.double()))) < 2e-5
+    assert abs(float(total) - float(ref_total)) < 2e-5
+    assert h.rel_inf(x.grad.cpu(), xr.grad.float()) < 1e-3
+
+
+def test_fused_photometric_loss_golden_from_reference():
+    """Directly against values the reference's own l1_loss/ssim produced (tests/golden/loss.npz)."""
+    import numpy as np, os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "loss.npz"))
+    dev = torch.device("cuda:0")
+    for tag in ("a", "b"):
+        x = torch.tensor(z[f"{tag}_img"]).to(dev).requires_grad_(True)
+        gt = torch.tensor(z[f"{tag}_gt"]).to(dev)
+        mask = torch.tensor(z[f"{tag}_mask"]).to(dev) if f"{tag}_mask" in z else None
+        total, l1, ss = gg.photometric_loss(x, gt, mask, 0.2)
+        total.backward()
+        assert abs(float(l1) - float(z[f"{tag}_l1"])) < 1e-6 and abs(float(ss) - float(z[f"{tag}_ssim"])) < 2e-5
+        ref = torch.tensor(z[f"{tag}_grad"])
+        assert float((x.grad.cpu() - ref).abs().max()) <= 1e-3 * float(ref.abs().max())

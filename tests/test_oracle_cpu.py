@@ -256,3 +256,20 @@ def test_mesh_bound_state_restatement():
     assert torch.allclose(Rq, R, atol=1e-5)                                  # quat <-> matrix consistent
     c = m.mesh_v[m.mesh_f].mean(1)
     assert torch.allclose(m.face_center, c)
+
+
+def test_loss_oracle_matches_reference_l1_and_ssim():
+    """oracle/loss_oracle.py vs values/gradients produced by the reference's utils/loss_utils.py (tests/golden/loss.npz)."""
+    from oracle import loss_oracle as lo
+    z = np.load(os.path.join(GOLD, "loss.npz"))
+    for tag in ("a", "b"):
+        img = torch.tensor(z[f"{tag}_img"]).requires_grad_(True)
+        gt = torch.tensor(z[f"{tag}_gt"])
+        mask = torch.tensor(z[f"{tag}_mask"]) if f"{tag}_mask" in z else None
+        assert abs(float(lo.l1_loss(img, gt, mask)) - float(z[f"{tag}_l1"])) < 1e-6
+        assert abs(float(lo.ssim(img, gt, mask)) - float(z[f"{tag}_ssim"])) < 1e-5
+        total = lo.total_loss(img, gt, mask, 0.2)
+        assert abs(float(total) - float(z[f"{tag}_total"])) < 1e-5
+        total.backward()
+        ref = torch.tensor(z[f"{tag}_grad"])
+        assert float((img.grad - ref).abs().max()) <= 1e-3 * float(ref.abs().max())
