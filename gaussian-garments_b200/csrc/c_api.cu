@@ -391,17 +391,17 @@ int gg_mesh_bind_backward(int32_t num_vertices, int32_t num_faces, int32_t num_g
 int gg_photometric_workspace_bytes(int32_t width, int32_t height, size_t* map_bytes) {
     if (width < 0 || height < 0) return fail(GG_E_BADARG, "negative size");
     // two double accumulators + three partial-derivative maps [3,H,W] (the maps are untouched when with_ssim = 0)
-    if (map_bytes) *map_bytes = 3 * align_up((size_t)3 * width * height * sizeof(float)) + 256;
+    if (map_bytes) *map_bytes = 3 * align_up((size_t)3 * width * height * sizeof(float)) + 1024;
     return 0;
 }
 
 static void photometric_carve(void* ws, int W, int H, float** m1, float** m2, float** m3, double** sums) {
     const size_t plane = align_up((size_t)3 * W * H * sizeof(float));
     char* b = (char*)ws;
-    *sums = (double*)b;
-    *m1 = (float*)(b + 256);
-    *m2 = (float*)(b + 256 + plane);
-    *m3 = (float*)(b + 256 + 2 * plane);
+    *sums = (double*)b;                      // 2 x 64 double slots
+    *m1 = (float*)(b + 1024);
+    *m2 = (float*)(b + 1024 + plane);
+    *m3 = (float*)(b + 1024 + 2 * plane);
 }
 
 int gg_photometric_forward(int32_t width, int32_t height, const float* image, const float* gt, const float* mask,
@@ -413,7 +413,7 @@ int gg_photometric_forward(int32_t width, int32_t height, const float* image, co
     float *m1, *m2, *m3;
     double* sums;
     photometric_carve(map_ws, width, height, &m1, &m2, &m3, &sums);
-    GG_CUDA(cudaMemsetAsync(sums, 0, 2 * sizeof(double), s));
+    GG_CUDA(cudaMemsetAsync(sums, 0, 1024, s));
     {
         ScopedKernelTimer kt(K_LOSSFWD, s);
         if (!with_ssim) m1 = m2 = m3 = nullptr;      // L1 only: no partial-derivative maps

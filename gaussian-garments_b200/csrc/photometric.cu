@@ -20,6 +20,7 @@ constexpr int PT = 16;          // output tile edge
 constexpr int PH = 5;           // halo
 constexpr int PI = PT + 2 * PH; // 26
 constexpr float SSIM_C1 = 0.01f * 0.01f, SSIM_C2 = 0.03f * 0.03f;
+constexpr int PHOTO_SLOTS = 64;   // accumulator slots per sum (host adds them up)
 
 __device__ __forceinline__ float block_sum_256(float v, float* red) {
     v = warp_sum(v);
@@ -98,10 +99,25 @@ photometric_fwd_kernel(int W, int H, const float* __restrict__ img, const float*
     }
     const float tl1 = block_sum_256(l1, red);
     const float tss = block_sum_256(ss, red);
-    if (threadIdx.x == 0) {
-        atomicAdd(&sums[0], (double)tl1);
-        atomicAdd(&sums[1], (double)tss);
+    if (threadIdx.x == 0) {     // 64 accumulator slots per sum: 24k CTAs hammering one address serialise in L2
+        const int slot = (blockIdx.x + blockIdx.y * gridDim.x + blockIdx.z * 7) & (PHOTO_SLOTS - 1);
+        atomicAdd(&sums[slot], (double)tl1);
+        atomicAdd(&sums[PHOTO_SLOTS + slot], (double)tss);
     }
+}
+
+// lambda_dssim == 0: plain streaming |(image - gt) * mask| sum, no tiles, no halo
+__global__ void __launch_bounds__(256)
+photometric_l1_fwd_kernel(size_t n, size_t plane, const float* __restrict__ img, const float* __restrict__ gt,
+                          const float* __restrict__ mask, double* __restrict__ sums) {
+    __shared__ float red[8];
+    float acc = 0.f;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float mk = mask ? mask[i % plane] : 1.f;
+        acc += fabsf((img[i] - gt[i]) * mk);
+    }
+    const float t = block_sum_256(acc, red);
+    if (threadIdx.x == 0) atomicAdd(&sums[blockIdx.x & (PHOTO_SLOTS - 1)], (double)t);
 }
 
 // dL/dimage = mask * [ c_l1 * sign((img-gt)*mask) + c_ss * (conv(m1) + 2 x conv(m2) + y conv(m3)) ]
@@ -172,6 +188,11 @@ photometric_bwd_kernel(int W, int H, const float* __restrict__ img, const float*
 int launch_photometric_fwd(int W, int H, const float* img, const float* gt, const float* mask, float* m1, float* m2,
                            float* m3, double* sums, cudaStream_t s) {
     if (W <= 0 || H <= 0) return 0;
+    if (m1 == nullptr) {
+        const size_t plane = (size_t)W * H;
+        photometric_l1_fwd_kernel<<<148 * 8, 256, 0, s>>>(3 * plane, plane, img, gt, mask, sums);
+        return 1;
+    }
     dim3 grid((W + PT - 1) / PT, (H + PT - 1) / PT, 3);
     photometric_fwd_kernel<<<grid, 256, 0, s>>>(W, H, img, gt, mask, m1, m2, m3, sums);
     return 1;

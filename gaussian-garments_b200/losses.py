@@ -44,12 +44,12 @@ class _Photometric(torch.autograd.Function):
         di = dev.index if dev.index is not None else torch.cuda.current_device()
         wb = C.c_size_t()
         _capi.check(lib.gg_photometric_workspace_bytes(W, H, C.byref(wb)), "gg_photometric_workspace_bytes")
-        ws = torch.empty(wb.value if lambda_dssim != 0.0 else 256, dtype=torch.uint8, device=dev)
+        ws = torch.empty(wb.value if lambda_dssim != 0.0 else 1024, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             sp = torch.cuda.current_stream(dev).cuda_stream
             _capi.check(lib.gg_photometric_forward(W, H, img.data_ptr(), g.data_ptr(), None if m is None else m.data_ptr(),
                                                    ws.data_ptr(), 1 if lambda_dssim != 0.0 else 0, di, sp), "gg_photometric_forward")
-        sums = ws[:16].view(torch.float64)
+        sums = ws[:1024].view(torch.float64).view(2, 64).sum(dim=1)
         n = 3.0 * H * W
         l1 = (sums[0] / n).float()
         ssim_v = (sums[1] / n).float()

@@ -153,9 +153,9 @@ int gg_mesh_bind_backward(int32_t num_vertices, int32_t num_faces, int32_t num_g
 /* ---- fused photometric loss ("next" row N2) -------------------------------------------------
  * Replaces l1_loss(image, gt, mask) and ssim(image, gt, mask) of /root/reference/utils/loss_utils.py:17-69
  * as used at s2_registration.py:259-260 / s3_appearance.py:132-133.  image, gt: [3,H,W]; mask: [1,H,W]
- * or NULL.  Forward writes into map_ws: two double sums at offset 0 {sum |(image-gt)*mask|, sum of the SSIM
- * map} followed by the three partial-derivative maps the backward consumes.  l1_loss = sums[0]/(3HW),
- * ssim = sums[1]/(3HW); with_ssim = 0 (lambda_dssim == 0) skips the SSIM work, then coeff_ssim must be 0.
+ * or NULL.  Forward writes into map_ws: 2 x 64 double accumulator slots at offset 0 (slots 0..63 add up to
+ * sum |(image-gt)*mask|, slots 64..127 to the sum of the SSIM map) followed at byte 1024 by the three
+ * partial-derivative maps the backward consumes.  l1_loss = sum(slots 0..63)/(3HW), ssim = sum(slots 64..127)/(3HW); with_ssim = 0 (lambda_dssim == 0) skips the SSIM work, then coeff_ssim must be 0.
  * Backward: dL_dimage = coeff_l1 * d(sum|.|)/dimage + coeff_ssim * d(sum ssim)/dimage
  * (the caller folds 1/(3HW) and lambda_dssim into the two coefficients; `upstream_scalar`, a DEVICE float
  * or NULL, multiplies both -- the loss gradient never visits the host).                                  */

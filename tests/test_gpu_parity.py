@@ -534,3 +534,39 @@ def test_fused_photometric_loss_golden_from_reference():
         assert abs(float(l1) - float(z[f"{tag}_l1"])) < 1e-6 and abs(float(ss) - float(z[f"{tag}_ssim"])) < 2e-5
         ref = torch.tensor(z[f"{tag}_grad"])
         assert float((x.grad.cpu() - ref).abs().max()) <= 1e-3 * float(ref.abs().max())
+
+
+def test_debug_mode_synchronises_and_matches():
+    """raster_settings.debug=True (arguments/__init__.py:69): sync + error check after every launch; same results."""
+    st = gg.scenes.random_cloud(2000, seed=17)
+    cam = gg.scenes.cfg1_camera(160, 128)
+    grads = _upstream_grads(128, 160)
+    a = h.run_cuda(h.settings_for(cam, st, device=torch.device("cuda:0"), debug=False), st, grads)
+    b = h.run_cuda(h.settings_for(cam, st, device=torch.device("cuda:0"), debug=True), st, grads)
+    assert torch.equal(a["color"], b["color"]) and torch.equal(a["radii"], b["radii"])
+    assert h.rel_inf(a["grads"]["means3D"], b["grads"]["means3D"]) < 1e-4
+
+
+def test_concurrent_streams_and_threads():
+    """Re-entrancy: two host threads rendering different scenes on their own streams get the single-threaded results."""
+    import threading
+    dev = torch.device("cuda:0")
+    jobs = []
+    for seed in (3, 4):
+        st = gg.scenes.random_cloud(3000, seed=seed)
+        cam = gg.scenes.cfg1_camera(192, 160)
+        S = h.settings_for(cam, st, device=dev)
+        jobs.append((st, S, h.run_cuda(S, st)["color"]))
+    out = [None, None]
+
+    def work(k):
+        with torch.cuda.stream(torch.cuda.Stream(device=dev)):
+            for _ in range(3):
+                out[k] = h.run_cuda(jobs[k][1], jobs[k][0])["color"]
+            torch.cuda.current_stream().synchronize()
+
+    ts = [threading.Thread(target=work, args=(k,)) for k in range(2)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    for k in range(2):
+        assert torch.equal(out[k], jobs[k][2])
