@@ -32,7 +32,10 @@ emit_kernel(int N, int gx, const int32_t* __restrict__ radii, const uint2* __res
         x0 = r.x & 0xffff; y0 = r.x >> 16; x1 = r.y & 0xffff; y1 = r.y >> 16;
         key = ((uint64_t)__float_as_uint(depth[i]) << 32) | (uint32_t)i;
     }
-    const int nt = (x1 - x0) * (y1 - y0);
+    constexpr int COOP_TILES = 16;
+    const int nt_all = (x1 - x0) * (y1 - y0);
+    const bool big = nt_all > COOP_TILES;
+    const int nt = big ? 0 : nt_all;
     const int max_nt = __reduce_max_sync(FULL, nt);
     int tx = x0, ty = y0;
     for (int k = 0; k < max_nt; k++) {
@@ -48,6 +51,22 @@ emit_kernel(int N, int gx, const int32_t* __restrict__ radii, const uint2* __res
             if (slot < capacity) keys[slot] = key;
         }
         if (++tx == x1) { tx = x0; ty++; }
+    }
+    // large footprints: the whole warp emits one splat's instances, 32 tiles per step
+    unsigned bigmask = __ballot_sync(FULL, big);
+    while (bigmask) {
+        const int src = __ffs(bigmask) - 1;
+        bigmask &= bigmask - 1;
+        const int bx0 = __shfl_sync(FULL, x0, src), by0 = __shfl_sync(FULL, y0, src);
+        const int bx1 = __shfl_sync(FULL, x1, src), by1 = __shfl_sync(FULL, y1, src);
+        const uint32_t klo = __shfl_sync(FULL, (uint32_t)key, src), khi = __shfl_sync(FULL, (uint32_t)(key >> 32), src);
+        const uint64_t bkey = ((uint64_t)khi << 32) | klo;
+        const int w = bx1 - bx0, total = w * (by1 - by0);
+        for (int k = lane; k < total; k += 32) {
+            const int t = (by0 + k / w) * gx + bx0 + k % w;
+            const uint32_t slot = tile_offset[t] + atomicAdd(&tile_fill[t], 1u);
+            if (slot < capacity) keys[slot] = bkey;
+        }
     }
 }
 

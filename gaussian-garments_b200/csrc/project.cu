@@ -12,13 +12,17 @@
 namespace gg {
 
 // ---------------------------------------------------------------------------------------------
-// Every lane walks its own tile rectangle; iteration k of all lanes is matched so that lanes hitting
-// the same tile issue ONE red.add of their population count.  Must be called by full warps.
+// Per-tile instance counts.  Must be called by full warps.
+constexpr int COOP_TILES = 16;   // splats touching more tiles than this are walked by the whole warp
+
 __device__ __forceinline__ void tile_count_aggregated(bool live, int x0, int y0, int x1, int y1, int gx,
                                                       uint32_t* __restrict__ tile_count) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    const int nt = live ? (x1 - x0) * (y1 - y0) : 0;
+    const int nt_all = live ? (x1 - x0) * (y1 - y0) : 0;
+    const bool big = nt_all > COOP_TILES;
+    // small footprints: every lane walks its own rectangle, same-tile lanes share one red.add
+    const int nt = big ? 0 : nt_all;
     const int max_nt = __reduce_max_sync(FULL, nt);
     int tx = x0, ty = y0;
     for (int k = 0; k < max_nt; k++) {
@@ -27,6 +31,16 @@ __device__ __forceinline__ void tile_count_aggregated(bool live, int x0, int y0,
         const unsigned grp = __match_any_sync(FULL, t);
         if (valid && lane == __ffs(grp) - 1) atomicAdd(&tile_count[t], (uint32_t)__popc(grp));
         if (++tx == x1) { tx = x0; ty++; }
+    }
+    // large footprints (dense / close-up scenes): the warp walks one splat's tiles together, 32 tiles per step
+    unsigned bigmask = __ballot_sync(FULL, big);
+    while (bigmask) {
+        const int src = __ffs(bigmask) - 1;
+        bigmask &= bigmask - 1;
+        const int bx0 = __shfl_sync(FULL, x0, src), by0 = __shfl_sync(FULL, y0, src);
+        const int bx1 = __shfl_sync(FULL, x1, src), by1 = __shfl_sync(FULL, y1, src);
+        const int w = bx1 - bx0, total = w * (by1 - by0);
+        for (int k = lane; k < total; k += 32) atomicAdd(&tile_count[(by0 + k / w) * gx + bx0 + k % w], 1u);
     }
 }
 
