@@ -137,6 +137,7 @@ def run_reference(args, rank, world):
     cams = gg.scenes.ring_cameras(N_CAMS, width=args.width, height=args.height)
     g = torch.Generator().manual_seed(gg.scenes.SEED + 1)
     gt = torch.rand(3, args.height, args.width, generator=g)
+    c_oracle.set_num_threads(os.cpu_count() or 1)      # torchrun exports OMP_NUM_THREADS=1: use every host core
     cores = c_oracle.num_threads()
 
     def one(cam):
@@ -395,6 +396,7 @@ def _capi_last_K():
 def run_cpu_baseline(args, st, cams, gt):
     """Oracle port on the box's host cores, bounded sample of the same workload."""
     from oracle import c_oracle
+    c_oracle.set_num_threads(os.cpu_count() or 1)
     cores = c_oracle.num_threads()
     n = max(1, args.cpu_views)
 
