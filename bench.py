@@ -32,6 +32,14 @@ WORKLOAD = "cfg2: 300k mesh-bound Gaussians (synthetic cylinder template, 50k fa
 N_GAUSS, WIDTH, HEIGHT, N_CAMS = 300_000, 1920, 1080, 8
 
 
+def _host_cores() -> int:
+    """Cores this process may run on (affinity / cpuset aware; os.cpu_count() over-subscribes in containers)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -137,7 +145,7 @@ def run_reference(args, rank, world):
     cams = gg.scenes.ring_cameras(N_CAMS, width=args.width, height=args.height)
     g = torch.Generator().manual_seed(gg.scenes.SEED + 1)
     gt = torch.rand(3, args.height, args.width, generator=g)
-    c_oracle.set_num_threads(os.cpu_count() or 1)      # torchrun exports OMP_NUM_THREADS=1: use every host core
+    c_oracle.set_num_threads(_host_cores())            # torchrun exports OMP_NUM_THREADS=1: use every usable core
     cores = c_oracle.num_threads()
 
     def one(cam):
@@ -396,7 +404,7 @@ def _capi_last_K():
 def run_cpu_baseline(args, st, cams, gt):
     """Oracle port on the box's host cores, bounded sample of the same workload."""
     from oracle import c_oracle
-    c_oracle.set_num_threads(os.cpu_count() or 1)
+    c_oracle.set_num_threads(_host_cores())
     cores = c_oracle.num_threads()
     n = max(1, args.cpu_views)
 
