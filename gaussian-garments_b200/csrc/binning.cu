@@ -284,28 +284,41 @@ blend_fwd_lazy_kernel(const uint32_t* __restrict__ tile_offset, const uint64_t* 
                 p0[dst] = q0; p1[dst] = q1; p2[dst] = q2;
             }
             __syncthreads();
-            for (uint32_t j = 0; j < m; j++) {
-                if (__all_sync(0xffffffffu, done)) break;
-                const float4 cc = lds128(a1 + 16u * j);
-                if (!((__float_as_uint(cc.w) >> warp) & 1u)) continue;
-                const float4 a = lds128(a0 + 16u * j);
-                const float dx = a.x - fx, dy = a.y - fy;
-                const float e2 = dx * (a.z * dx + a.w * dy) + (cc.x * dy) * dy;
-                const float alpha = fminf(ALPHA_MAX, cc.y * ex2_approx(e2));
-                bool ok = !done && e2 <= 0.f && alpha >= ALPHA_MIN;
-                const float test_T = T * (1.f - alpha);
-                if (ok && test_T < T_STOP) {
-                    done = true;
-                    ok = false;
-                }
-                if (ok) {
-                    const float w = alpha * T;
-                    const float4 col = lds128(a2 + 16u * j);
-                    C0 += col.x * w; C1 += col.y * w; C2 += col.z * w;
-                    Dp += cc.z * w;
-                    Ac += w;
-                    T = test_T;
-                    last = processed + j + 1;
+            uint32_t mw[LZ_CHUNK / 32];                      // this warp's work list for the chunk (see blend_fwd.cu)
+#pragma unroll
+            for (int k = 0; k < LZ_CHUNK / 32; k++) {
+                const uint32_t e = (uint32_t)(k * 32 + lane);
+                const uint32_t wbits = (e < m) ? __float_as_uint(lds32(a1 + 16u * e + 12u)) : 0u;
+                mw[k] = __ballot_sync(0xffffffffu, (wbits >> warp) & 1u);
+            }
+            bool warp_done = false;
+#pragma unroll
+            for (int k = 0; k < LZ_CHUNK / 32; k++) {
+                uint32_t bits = mw[k];
+                while (bits && !warp_done) {
+                    if (__all_sync(0xffffffffu, done)) { warp_done = true; break; }
+                    const uint32_t j = (uint32_t)(k * 32 + __ffs(bits) - 1);
+                    bits &= bits - 1;
+                    const float4 cc = lds128(a1 + 16u * j);
+                    const float4 a = lds128(a0 + 16u * j);
+                    const float dx = a.x - fx, dy = a.y - fy;
+                    const float e2 = dx * (a.z * dx + a.w * dy) + (cc.x * dy) * dy;
+                    const float alpha = fminf(ALPHA_MAX, cc.y * ex2_approx(e2));
+                    bool ok = !done && e2 <= 0.f && alpha >= ALPHA_MIN;
+                    const float test_T = T * (1.f - alpha);
+                    if (ok && test_T < T_STOP) {
+                        done = true;
+                        ok = false;
+                    }
+                    if (ok) {
+                        const float w = alpha * T;
+                        const float4 col = lds128(a2 + 16u * j);
+                        C0 += col.x * w; C1 += col.y * w; C2 += col.z * w;
+                        Dp += cc.z * w;
+                        Ac += w;
+                        T = test_T;
+                        last = processed + j + 1;
+                    }
                 }
             }
             processed += m;

@@ -15,7 +15,7 @@ constexpr int FWD_BATCH = 128;
 constexpr int FWD_STAGES = 3;
 
 #ifndef GG_FWD_MINB
-#define GG_FWD_MINB 6
+#define GG_FWD_MINB 5
 #endif
 __global__ void __launch_bounds__(TILE_PIX, GG_FWD_MINB)
 blend_fwd_kernel(const uint32_t* __restrict__ tile_offset, const float4* __restrict__ p0,
@@ -74,31 +74,46 @@ blend_fwd_kernel(const uint32_t* __restrict__ tile_offset, const float4* __restr
         {
             const int cnt = min(FWD_BATCH, (int)n - b * FWD_BATCH);
             const uint32_t a0 = smem_u32(&s0[st][0]), a1 = smem_u32(&s1[st][0]), a2 = smem_u32(&s2[st][0]);
-            for (int j = 0; j < cnt; j++) {
-                if (__all_sync(0xffffffffu, done)) break;
-                const float4 c = lds128(a1 + 16u * j);
-                if (!((__float_as_uint(c.w) >> warp) & 1u)) continue;    // warp-uniform: splat cannot reach this 8x4 block
-                const float4 a = lds128(a0 + 16u * j);
-                const float dx = a.x - fx, dy = a.y - fy;
-                // log2-domain exponent: A' dx^2 + B' dx dy + C' dy^2  (= power * log2 e)
-                const float p2 = dx * (a.z * dx + a.w * dy) + (c.x * dy) * dy;
-                const float alpha = fminf(ALPHA_MAX, c.y * ex2_approx(p2));
-                bool ok = !done && p2 <= 0.f && alpha >= ALPHA_MIN;
-                const float test_T = T * (1.f - alpha);
-                if (ok && test_T < T_STOP) {
-                    done = true;
-                    ok = false;
-                }
-                if (ok) {
-                    const float w = alpha * T;
-                    const float4 col = lds128(a2 + 16u * j);
-                    C0 += col.x * w;
-                    C1 += col.y * w;
-                    C2 += col.z * w;
-                    Dp += c.z * w;
-                    Ac += w;
-                    T = test_T;
-                    last = (uint32_t)(b * FWD_BATCH + j + 1);
+            // Work list of this warp for the batch: bit `warp` of every record's warp-overlap mask, gathered with
+            // four ballots; records whose alpha >= 1/255 bounding box misses this warp's 8x4 block cost nothing.
+            uint32_t mw[FWD_BATCH / 32];
+#pragma unroll
+            for (int k = 0; k < FWD_BATCH / 32; k++) {
+                const int e = k * 32 + lane;
+                const uint32_t wbits = (e < cnt) ? __float_as_uint(lds32(a1 + 16u * e + 12u)) : 0u;
+                mw[k] = __ballot_sync(0xffffffffu, (wbits >> warp) & 1u);
+            }
+            bool warp_done = false;
+#pragma unroll
+            for (int k = 0; k < FWD_BATCH / 32; k++) {
+                uint32_t m = mw[k];
+                while (m && !warp_done) {
+                    if (__all_sync(0xffffffffu, done)) { warp_done = true; break; }   // also re-converges the warp
+                    const int j = k * 32 + __ffs(m) - 1;
+                    m &= m - 1;
+                    const float4 c = lds128(a1 + 16u * j);
+                    const float4 a = lds128(a0 + 16u * j);
+                    const float dx = a.x - fx, dy = a.y - fy;
+                    // log2-domain exponent: A' dx^2 + B' dx dy + C' dy^2  (= power * log2 e)
+                    const float p2 = dx * (a.z * dx + a.w * dy) + (c.x * dy) * dy;
+                    const float alpha = fminf(ALPHA_MAX, c.y * ex2_approx(p2));
+                    bool ok = !done && p2 <= 0.f && alpha >= ALPHA_MIN;
+                    const float test_T = T * (1.f - alpha);
+                    if (ok && test_T < T_STOP) {
+                        done = true;
+                        ok = false;
+                    }
+                    if (ok) {
+                        const float w = alpha * T;
+                        const float4 col = lds128(a2 + 16u * j);
+                        C0 += col.x * w;
+                        C1 += col.y * w;
+                        C2 += col.z * w;
+                        Dp += c.z * w;
+                        Ac += w;
+                        T = test_T;
+                        last = (uint32_t)(b * FWD_BATCH + j + 1);
+                    }
                 }
             }
         }

@@ -326,22 +326,41 @@ __device__ __forceinline__ void pack_record(uint64_t key, const float2* __restri
     const float2 m = xy[id];
     const float4 co = conic_o[id];
     const float r = rgb[3 * (size_t)id], g = rgb[3 * (size_t)id + 1], b = rgb[3 * (size_t)id + 2];
-    // warp-overlap mask from the alpha >= 1/255 ellipse's bounding box (covariance = conic^-1)
+    // warp-overlap mask: bit w set iff some point of warp w's 8x4 pixel-centre box can reach alpha >= 1/255, i.e.
+    // min over the box of f(d) = (A dx^2 + 2 B dx dy + C dy^2)/2 is <= tau = ln(255 o).  First the ellipse's bounding
+    // box (cheap reject), then the exact box minimum of the convex quadratic (centre inside -> 0, else the best of
+    // the four edge minima).  tau is inflated by 0.1 % + 1e-3 so rounding in the blend's exponent cannot matter.
     uint32_t wmask = 0;
     const float dc = co.x * co.z - co.y * co.y;
     float ex, ey;
-    if (dc > 0.f) {
+    if (dc > 0.f && co.x > 0.f && co.z > 0.f) {
         if (alpha_extent(co.w, co.z / dc, co.x / dc, ex, ey)) {
-            const float lx0 = m.x - ex - tile_x, lx1 = m.x + ex - tile_x;     // bbox in tile-local pixels
-            const float ly0 = m.y - ey - tile_y, ly1 = m.y + ey - tile_y;
-            const uint32_t xb = ((lx0 <= 7.f && lx1 >= 0.f) ? 1u : 0u) | ((lx0 <= 15.f && lx1 >= 8.f) ? 2u : 0u);
-            uint32_t yb = 0;
+            const float tau = logf(255.0f * co.w) * 1.001f + 1e-3f;
+            const float cx = m.x - tile_x, cy = m.y - tile_y;                       // centre in tile-local pixels
+            const float A = co.x, B = co.y, C = co.z, iA = 1.0f / co.x, iC = 1.0f / co.z;
 #pragma unroll
-            for (int q = 0; q < 4; q++)
-                if (ly0 <= (float)(4 * q + 3) && ly1 >= (float)(4 * q)) yb |= 1u << q;
+            for (int w = 0; w < 8; w++) {
+                const float X0 = (float)((w & 1) * 8), X1 = X0 + 7.f, Y0 = (float)((w >> 1) * 4), Y1 = Y0 + 3.f;
+                if (cx + ex < X0 || cx - ex > X1 || cy + ey < Y0 || cy - ey > Y1) continue;      // bounding-box reject
+                bool hit = (cx >= X0 && cx <= X1 && cy >= Y0 && cy <= Y1);
+                if (!hit) {
+                    float fmin_ = 3.0e38f;
 #pragma unroll
-            for (int w = 0; w < 8; w++)
-                if (((xb >> (w & 1)) & 1u) && ((yb >> (w >> 1)) & 1u)) wmask |= 1u << w;
+                    for (int e = 0; e < 2; e++) {                                   // vertical edges x = X0 / X1
+                        const float u = (e ? X1 : X0) - cx;
+                        const float v = fminf(fmaxf(cy - B * u * iC, Y0), Y1) - cy;
+                        fmin_ = fminf(fmin_, 0.5f * (A * u * u + C * v * v) + B * u * v);
+                    }
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {                                   // horizontal edges y = Y0 / Y1
+                        const float v = (e ? Y1 : Y0) - cy;
+                        const float u = fminf(fmaxf(cx - B * v * iA, X0), X1) - cx;
+                        fmin_ = fminf(fmin_, 0.5f * (A * u * u + C * v * v) + B * u * v);
+                    }
+                    hit = fmin_ <= tau;
+                }
+                if (hit) wmask |= 1u << w;
+            }
         }
     } else {
         wmask = 0xffu;   // degenerate conic: no culling information
