@@ -88,3 +88,29 @@ def test_bucket_views_are_aligned_and_disjoint():
     b.view(0).fill_(1.0)
     b.view(1).fill_(2.0)
     assert float(b.view(0).sum()) == 21.0 and float(b.view(1).sum()) == 2.0 * 7 * 48
+
+
+def test_bucket_adopt_copies_foreign_grads_and_zero_fills_missing():
+    """adopt(): a .grad that autograd cloned (not a bucket view) is copied in; a missing .grad becomes zeros."""
+    params = [torch.zeros(5, 3, requires_grad=True), torch.zeros(5, 1, requires_grad=True)]
+    b = GradBucket(params, 2, register=False)
+    b.flat.fill_(7.0)
+    params[0].grad = torch.full((5, 3), 2.0)          # foreign tensor
+    params[1].grad = None
+    b.adopt()
+    assert params[0].grad.data_ptr() == b.view(0).data_ptr() and float(b.view(0).sum()) == 30.0
+    assert params[1].grad.data_ptr() == b.view(1).data_ptr() and float(b.view(1).abs().sum()) == 0.0
+
+
+def test_grad_sink_registry_roundtrip():
+    from gaussian_garments_b200 import rasterizer
+    params = [torch.zeros(4, 3, requires_grad=True)]
+    b = GradBucket(params, 1)
+    try:
+        ent = rasterizer._sink_of(params[0])
+        assert ent is not None and ent[0] is b.flat and ent[2] == (4, 3)
+        assert rasterizer._sink_of(torch.zeros(4, 3)) is None          # unknown tensor: no sink
+        assert rasterizer._sink_of(params[0][:2]) is None or rasterizer._sink_of(params[0][:2])[2] != (2, 3)
+    finally:
+        b.unregister()
+    assert rasterizer._sink_of(params[0]) is None
