@@ -43,6 +43,16 @@ def lib():
         _LIB.ggo_num_rendered.argtypes = [C.c_void_p]
         _LIB.ggo_free.argtypes = [C.c_void_p]
         _LIB.ggo_num_threads.restype = C.c_int
+        # every entry point gets explicit argtypes: without them ctypes passes Python ints as 32-bit C ints,
+        # which truncates / sign-extends a state handle as soon as the heap grows past 2 GB
+        vp = C.c_void_p
+        _LIB.ggo_forward.argtypes = [C.POINTER(_Params)] + [vp] * 8 + [vp] * 5 + [C.c_float, C.POINTER(vp)]
+        _LIB.ggo_backward.argtypes = [vp] * 12
+        _LIB.ggo_get_geom.argtypes = [vp] * 6
+        _LIB.ggo_get_geom.restype = C.c_int
+        _LIB.ggo_get_binning.argtypes = [vp] * 5
+        _LIB.ggo_get_binning.restype = C.c_int
+        _LIB.ggo_set_num_threads.argtypes = [C.c_int]
     return _LIB
 
 
@@ -85,7 +95,7 @@ class Context:
         N = self.N
         xy = torch.zeros(N, 2); depth = torch.zeros(N); conic_o = torch.zeros(N, 4)
         rgb = torch.zeros(N, 3); rect = torch.zeros(N, 4, dtype=torch.int32)
-        lib().ggo_get_geom(self.h, _p(xy), _p(depth), _p(conic_o), _p(rgb), _p(rect))
+        lib().ggo_get_geom(C.c_void_p(self.h), _p(xy), _p(depth), _p(conic_o), _p(rgb), _p(rect))
         return dict(xy=xy, depth=depth, conic_opacity=conic_o, rgb=rgb, rect=rect)
 
     def binning(self):
@@ -95,7 +105,7 @@ class Context:
         inst = torch.zeros(max(K, 1), dtype=torch.int32)
         nc = torch.zeros(self.H, self.W, dtype=torch.int32)
         ft = torch.zeros(self.H, self.W)
-        lib().ggo_get_binning(self.h, _p(off), _p(inst), _p(nc), _p(ft))
+        lib().ggo_get_binning(C.c_void_p(self.h), _p(off), _p(inst), _p(nc), _p(ft))
         return dict(tile_off=off, inst=inst[:K], n_contrib=nc, final_T=ft)
 
     def backward(self, dL_dcolor, dL_ddepth=None, dL_dalpha=None):
@@ -156,4 +166,4 @@ def num_threads() -> int:
 
 
 def set_num_threads(n: int):
-    lib().ggo_set_num_threads(C.c_int(n))
+    lib().ggo_set_num_threads(int(n))
