@@ -48,6 +48,8 @@ def lib():
         vp = C.c_void_p
         _LIB.ggo_forward.argtypes = [C.POINTER(_Params)] + [vp] * 8 + [vp] * 5 + [C.c_float, C.POINTER(vp)]
         _LIB.ggo_backward.argtypes = [vp] * 12
+        _LIB.ggo_backward_forward_order.argtypes = [vp] * 12
+        _LIB.ggo_backward_forward_order.restype = C.c_int
         _LIB.ggo_get_geom.argtypes = [vp] * 6
         _LIB.ggo_get_geom.restype = C.c_int
         _LIB.ggo_get_binning.argtypes = [vp] * 5
@@ -108,7 +110,7 @@ class Context:
         lib().ggo_get_binning(C.c_void_p(self.h), _p(off), _p(inst), _p(nc), _p(ft))
         return dict(tile_off=off, inst=inst[:K], n_contrib=nc, final_T=ft)
 
-    def backward(self, dL_dcolor, dL_ddepth=None, dL_dalpha=None):
+    def backward(self, dL_dcolor, dL_ddepth=None, dL_dalpha=None, forward_order=False):
         N, M = self.N, self.M
         gc, gd, ga = _f32(dL_dcolor), _f32(dL_ddepth), _f32(dL_dalpha)
         out = dict(
@@ -119,7 +121,8 @@ class Context:
             scales=None if self.has_cov else torch.zeros(N, 3),
             rotations=None if self.has_cov else torch.zeros(N, 4),
             cov3D_precomp=torch.zeros(N, 6) if self.has_cov else None)
-        rc = lib().ggo_backward(C.c_void_p(self.h), _p(gc), _p(gd), _p(ga), _p(out["means3D"]), _p(out["means2D"]),
+        fn = lib().ggo_backward_forward_order if forward_order else lib().ggo_backward
+        rc = fn(C.c_void_p(self.h), _p(gc), _p(gd), _p(ga), _p(out["means3D"]), _p(out["means2D"]),
                                 _p(out["shs"]), _p(out["colors_precomp"]), _p(out["opacities"]),
                                 _p(out["scales"]), _p(out["rotations"]), _p(out["cov3D_precomp"]))
         if rc != 0:

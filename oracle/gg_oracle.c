@@ -367,9 +367,10 @@ int ggo_get_binning(const ggo_state* s, int64_t* tile_off, uint32_t* inst, int32
 
 /* ------------------------------------------------------------------------------------------- */
 /* a10 + a11.  Any output pointer may be NULL. dL_dmeans2D is [N,3] (z = 0). */
-int ggo_backward(const ggo_state* s, const float* dL_dcolor, const float* dL_ddepth, const float* dL_dalpha,
-                 float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dshs, float* dL_dcolors_precomp,
-                 float* dL_dopacities, float* dL_dscales, float* dL_drotations, float* dL_dcov3D) {
+static int backward_impl(const ggo_state* s, int forward_order, const float* dL_dcolor, const float* dL_ddepth,
+                         const float* dL_dalpha, float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dshs,
+                         float* dL_dcolors_precomp, float* dL_dopacities, float* dL_dscales, float* dL_drotations,
+                         float* dL_dcov3D) {
     const ggo_params p = s->p;
     const int N = p.N, W = p.W, H = p.H, gx = s->gx, T = s->T;
     const size_t P = (size_t)W * H;
@@ -406,6 +407,60 @@ int ggo_backward(const ggo_state* s, const float* dL_dcolor, const float* dL_dde
                     const float bg_dot = p.bg[0] * gC[0] + p.bg[1] * gC[1] + p.bg[2] * gC[2];
                     float accum_c[3] = {0, 0, 0}, accum_d = 0, accum_a = 0;
                     float last_alpha = 0, last_c[3] = {0, 0, 0}, last_d = 0;
+                    if (forward_order) {
+                        /* Front-to-back formulation (what a per-Gaussian-parallel backward needs: no "colour behind"
+                         * recurrence, only running prefixes and the pixel's totals).  With v_i = (c_i, z_i, 1),
+                         * upstream g = (gC, gD, gA), w_i = alpha_i T_i, U_i = sum_{j<=i} w_j (g.v_j) and
+                         * TOT = sum_j w_j (g.v_j) + T_final (gC.bg):
+                         *     dL/dalpha_i = T_i (g.v_i) - (TOT - U_i) / (1 - alpha_i)                          */
+                        double tot = (double)T_final * bg_dot;
+                        {
+                            float Tt = 1.f;
+                            for (int64_t j = 0; j < s->n_contrib[pid]; j++) {
+                                const uint32_t g = s->inst[o + j];
+                                const float dx = s->xy[2 * (size_t)g] - (float)px, dy = s->xy[2 * (size_t)g + 1] - (float)py;
+                                const float* co = s->conic_o + 4 * (size_t)g;
+                                const float power = -0.5f * (co[0] * dx * dx + co[2] * dy * dy) - co[1] * dx * dy;
+                                if (power > 0.f) continue;
+                                const float alpha = fminf(ALPHA_MAX, co[3] * expf(power));
+                                if (alpha < ALPHA_MIN) continue;
+                                const float* rgb = s->rgb + 3 * (size_t)g;
+                                const float gv = rgb[0] * gC[0] + rgb[1] * gC[1] + rgb[2] * gC[2] + s->depth[g] * gD + gA;
+                                tot += (double)(alpha * Tt) * gv;
+                                Tt *= (1.f - alpha);
+                            }
+                        }
+                        float Tt = 1.f;
+                        double upto = 0.0;
+                        for (int64_t j = 0; j < s->n_contrib[pid]; j++) {
+                            const uint32_t g = s->inst[o + j];
+                            const float dx = s->xy[2 * (size_t)g] - (float)px, dy = s->xy[2 * (size_t)g + 1] - (float)py;
+                            const float* co = s->conic_o + 4 * (size_t)g;
+                            const float power = -0.5f * (co[0] * dx * dx + co[2] * dy * dy) - co[1] * dx * dy;
+                            if (power > 0.f) continue;
+                            const float G = expf(power);
+                            const float alpha = fminf(ALPHA_MAX, co[3] * G);
+                            if (alpha < ALPHA_MIN) continue;
+                            const float w = alpha * Tt;
+                            const float* rgb = s->rgb + 3 * (size_t)g;
+                            const float gv = rgb[0] * gC[0] + rgb[1] * gC[1] + rgb[2] * gC[2] + s->depth[g] * gD + gA;
+                            upto += (double)w * gv;
+                            const float dL_dalpha_ = Tt * gv - (float)((tot - upto) / (double)(1.f - alpha));
+                            double* L = loc + (size_t)j * 10;
+                            L[6] += (double)(w * gC[0]); L[7] += (double)(w * gC[1]); L[8] += (double)(w * gC[2]);
+                            L[9] += (double)(w * gD);
+                            const float dL_dG = co[3] * dL_dalpha_;
+                            const float gdx = G * dx, gdy = G * dy;
+                            L[0] += (double)(dL_dG * (-gdx * co[0] - gdy * co[1]) * 0.5f * W);
+                            L[1] += (double)(dL_dG * (-gdy * co[2] - gdx * co[1]) * 0.5f * H);
+                            L[2] += (double)(-0.5f * gdx * dx * dL_dG);
+                            L[3] += (double)(-gdx * dy * dL_dG);
+                            L[4] += (double)(-0.5f * gdy * dy * dL_dG);
+                            L[5] += (double)(G * dL_dalpha_);
+                            Tt *= (1.f - alpha);
+                        }
+                        continue;
+                    }
                     for (int64_t j = s->n_contrib[pid] - 1; j >= 0; j--) {
                         const uint32_t g = s->inst[o + j];
                         const float dx = s->xy[2 * (size_t)g] - (float)px, dy = s->xy[2 * (size_t)g + 1] - (float)py;
@@ -645,6 +700,24 @@ int ggo_backward(const ggo_state* s, const float* dL_dcolor, const float* dL_dde
     }
     free(acc);
     return 0;
+}
+
+int ggo_backward(const ggo_state* s, const float* dL_dcolor, const float* dL_ddepth, const float* dL_dalpha,
+                 float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dshs, float* dL_dcolors_precomp,
+                 float* dL_dopacities, float* dL_dscales, float* dL_drotations, float* dL_dcov3D) {
+    return backward_impl(s, 0, dL_dcolor, dL_ddepth, dL_dalpha, dL_dmeans3D, dL_dmeans2D, dL_dshs, dL_dcolors_precomp,
+                         dL_dopacities, dL_dscales, dL_drotations, dL_dcov3D);
+}
+
+/* Same gradients through the front-to-back formulation (prefix sums + pixel totals instead of the back-to-front
+ * "colour behind" recurrence).  Kept as a checked statement of the math a per-Gaussian-parallel backward kernel
+ * would use; tests/test_oracle_cpu.py compares it with ggo_backward. */
+int ggo_backward_forward_order(const ggo_state* s, const float* dL_dcolor, const float* dL_ddepth,
+                               const float* dL_dalpha, float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dshs,
+                               float* dL_dcolors_precomp, float* dL_dopacities, float* dL_dscales,
+                               float* dL_drotations, float* dL_dcov3D) {
+    return backward_impl(s, 1, dL_dcolor, dL_ddepth, dL_dalpha, dL_dmeans3D, dL_dmeans2D, dL_dshs, dL_dcolors_precomp,
+                         dL_dopacities, dL_dscales, dL_drotations, dL_dcov3D);
 }
 
 int ggo_num_threads(void) {

@@ -273,3 +273,18 @@ def test_loss_oracle_matches_reference_l1_and_ssim():
         total.backward()
         ref = torch.tensor(z[f"{tag}_grad"])
         assert float((img.grad - ref).abs().max()) <= 1e-3 * float(ref.abs().max())
+
+
+def test_forward_order_backward_formulation_equals_back_to_front():
+    """dL/dalpha_i = T_i (g.v_i) - (TOT - U_i)/(1 - alpha_i) (prefix sums + pixel totals) reproduces the
+    back-to-front 'colour behind' recurrence: the formulation a per-Gaussian-parallel backward would use."""
+    st = gg.scenes.random_cloud(3000, seed=21)
+    cam = gg.scenes.cfg1_camera(192, 144)
+    S = h.settings_for(cam, st, device="cpu")
+    grads = _grads_for(cam)
+    ref = h.run_c_oracle(S, st, None)
+    a = ref["ctx"].backward(*grads)
+    b = ref["ctx"].backward(*grads, forward_order=True)
+    for k, v in a.items():
+        if v is not None:
+            assert h.rel_inf(b[k], v) < 2e-5, k
