@@ -57,6 +57,12 @@ int cuda_fail(cudaError_t e, const char* where) {
         if (_e != cudaSuccess) return cuda_fail(_e, #call);   \
     } while (0)
 
+// environment switches are read ONCE per process (function-local statics at the call sites)
+inline bool env_is(const char* name, const char* value) {
+    const char* e = getenv(name);
+    return e && !strcmp(e, value);
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 int check_view(const gg_view* v) {
@@ -232,13 +238,15 @@ int gg_forward_render(const gg_view* view, const gg_inputs* in, const void* geom
     record_layout(record_ws, instance_capacity, &r);
     image_layout(image_ws, (int64_t)P, &img);
     const uint32_t cap = (uint32_t)instance_capacity;
+    // emit cursors start at zero (also makes a re-run after GG_E_OVERFLOW-style capacity growth self-contained)
+    GG_CUDA(cudaMemsetAsync(t.fill, 0, (size_t)T * sizeof(uint32_t), s));
     { ScopedKernelTimer kt(K_EMIT, s); g_launches += launch_emit(*view, g, t, radii, (uint64_t*)key_ws, cap, s); }
     GG_AFTER("emit_kernel");
     // Forward path: "tma" = per-tile full sort + pack, then the bulk-TMA streamed blend;
     //               "lazy" = fused bucket-sort + pack + blend that stops at tile saturation (dense scenes).
     // auto: lazy when some tile holds more instances than the default shared-memory sort handles.
     bool lazy = max_tile_instances > 4096;
-    if (const char* e = getenv("GG_FWD_PATH")) {
+    if (const char* e = getenv("GG_FWD_PATH")) {   // test/diagnostic override (tests flip it between calls)
         if (!strcmp(e, "lazy")) lazy = true;
         else if (!strcmp(e, "tma")) lazy = false;
     }
@@ -280,7 +288,16 @@ int gg_backward(const gg_view* view, const gg_inputs* in, const void* tile_ws, c
     record_layout(const_cast<void*>(record_ws), instance_capacity, &r);
     image_layout(const_cast<void*>(image_ws), (int64_t)view->image_width * view->image_height, &img);
     accum_layout(accum_ws, view->num_gaussians, &acc);
-    { ScopedKernelTimer kt(K_BLENDBWD, s); g_launches += launch_blend_bwd(*view, *in, t, r, img, dL_dcolor, dL_ddepth, dL_dalpha, acc, s); }
+    GG_CUDA(cudaMemsetAsync(accum_ws, 0, accum_layout(nullptr, view->num_gaussians, nullptr), s));
+    {
+        // "v2" (default): pixel-parallel evaluation + splat-parallel moment reduction (blend_bwd2.cu);
+        // "v1": round 1's shuffle reduce-scatter kernel (blend_bwd.cu), kept for A/B measurements.
+        static const bool bwd_v1 = env_is("GG_BWD_PATH", "v1");
+        static const int bwd2_minb = env_is("GG_BWD2_MINB", "3") ? 3 : 4;
+        ScopedKernelTimer kt(K_BLENDBWD, s);
+        g_launches += bwd_v1 ? launch_blend_bwd(*view, *in, t, r, img, dL_dcolor, dL_ddepth, dL_dalpha, acc, s)
+                             : launch_blend_bwd2(*view, *in, t, r, img, dL_dcolor, dL_ddepth, dL_dalpha, acc, bwd2_minb, s);
+    }
     GG_AFTER("blend_bwd_kernel");
     {
         ScopedKernelTimer kt(K_PREBWD, s);
@@ -323,6 +340,26 @@ int gg_debug_read_geom(const gg_view* view, const void* geom_ws, float* xy, floa
     if (rect) {   // unpack on the host side is not possible for device destinations: copy packed pairs
         GG_CUDA(cudaMemcpyAsync(rect, g.rect, N * 8, k, s));
     }
+    return 0;
+}
+
+int gg_debug_read_binning(const gg_view* view, const void* tile_ws, const void* record_ws, int64_t instance_capacity,
+                          uint32_t* tile_offsets, uint32_t* sorted_ids, int device, void* stream) {
+    if (int rc = check_view(view)) return rc;
+    if (!tile_ws || !record_ws) return fail(GG_E_BADARG, "NULL workspace");
+    if (instance_capacity < 0 || instance_capacity > 0xfffffff0ll) return fail(GG_E_BADARG, "instance_capacity out of range");
+    GG_CUDA(cudaSetDevice(device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const int gx = (view->image_width + TILE - 1) / TILE, gy = (view->image_height + TILE - 1) / TILE;
+    const int T = gx * gy;
+    TileWS t;
+    RecordWS r;
+    tile_layout(const_cast<void*>(tile_ws), T, &t);
+    record_layout(const_cast<void*>(record_ws), instance_capacity, &r);
+    if (tile_offsets) GG_CUDA(cudaMemcpyAsync(tile_offsets, t.offset, (size_t)(T + 1) * 4, cudaMemcpyDefault, s));
+    if (sorted_ids && instance_capacity > 0)   // ids sit in the .w lane of plane p2: strided gather
+        GG_CUDA(cudaMemcpy2DAsync(sorted_ids, 4, reinterpret_cast<const char*>(r.p2) + 12, 16, 4,
+                                  (size_t)instance_capacity, cudaMemcpyDefault, s));
     return 0;
 }
 

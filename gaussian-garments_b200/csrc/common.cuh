@@ -140,6 +140,9 @@ int launch_blend_fwd_lazy(const gg_view& v, const gg_inputs& in, const GeomWS& g
 int launch_blend_bwd(const gg_view& v, const gg_inputs& in, const TileWS& t, const RecordWS& r, const ImageWS& img,
                      const float* dL_dcolor, const float* dL_ddepth, const float* dL_dalpha, const AccumWS& acc,
                      cudaStream_t s);
+int launch_blend_bwd2(const gg_view& v, const gg_inputs& in, const TileWS& t, const RecordWS& r, const ImageWS& img,
+                      const float* dL_dcolor, const float* dL_ddepth, const float* dL_dalpha, const AccumWS& acc,
+                      int min_blocks, cudaStream_t s);
 int launch_preprocess_bwd(const gg_view& v, const gg_inputs& in, const int32_t* radii, const AccumWS& acc,
                           float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dshs, float* dL_dcolors,
                           float* dL_dopacities, float* dL_dscales, float* dL_drotations, float* dL_dcov3D,

@@ -5,7 +5,7 @@ s3_appearance.py:107-124) and has no distributed code.  BASELINE.json's multi-GP
 views one per rank; the only exchange on the path is the sum of the per-view parameter gradients.
 
 Design: all parameter gradients live in ONE contiguous fp32 buffer.  The rasterizer's
-backward kernel writes its outputs straight into views of that buffer (see `rasterizer.grad_sinks`),
+backward kernel writes its outputs straight into views of that buffer (see `rasterizer.GradSink`),
 autograd's AccumulateGrad adopts those views as `.grad` without a copy, and a single
 `all_reduce(AVG)` over the flat buffer is the step's only collective -- no per-tensor launches, no
 staging copies.  NVSwitch gives every rank uniform bandwidth, so no topology tuning is needed.
@@ -38,14 +38,20 @@ class GradBucket:
 
     # -- zero-copy hand-off to the rasterizer's backward ------------------------------------
     def register(self):
-        from . import rasterizer
+        from .rasterizer import GradSink
         for p, o in zip(self.params, self.offsets):
-            rasterizer.grad_sinks[p.data_ptr()] = (self.flat, o, tuple(p.shape))
+            p._gg_sink = GradSink(self.flat, o, p.shape)      # on the tensor object: cannot alias a recycled address
 
     def unregister(self):
-        from . import rasterizer
         for p in self.params:
-            rasterizer.grad_sinks.pop(p.data_ptr(), None)
+            if getattr(p, "_gg_sink", None) is not None and p._gg_sink.flat is self.flat:
+                del p._gg_sink
+
+    def __del__(self):
+        try:
+            self.unregister()
+        except Exception:
+            pass
 
     def view(self, i: int) -> torch.Tensor:
         p, o = self.params[i], self.offsets[i]
@@ -56,6 +62,9 @@ class GradBucket:
         no memset is needed for sink-backed parameters."""
         for p in self.params:
             p.grad = None
+            ent = getattr(p, "_gg_sink", None)
+            if ent is not None:
+                ent.armed = True       # one zero-copy hand-off per zero(); later backwards accumulate into it
 
     def adopt(self):
         """Make sure every param's .grad aliases the bucket (copies in the rare case autograd cloned)."""

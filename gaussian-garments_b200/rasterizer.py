@@ -19,6 +19,7 @@ from __future__ import annotations
 
 import ctypes as C
 import threading
+import weakref
 from typing import NamedTuple, Optional
 
 import torch
@@ -46,20 +47,43 @@ class GaussianRasterizationSettings(NamedTuple):
 # one pinned word per (thread, device) for the num_rendered read-back
 _tls = threading.local()
 
-# data_ptr of an input tensor -> (flat fp32 buffer, element offset, shape): when present, backward
-# writes that input's gradient straight into the flat buffer (dist.GradBucket, zero-copy all-reduce).
-grad_sinks = {}
-
 LAST_NUM_RENDERED = 0   # K of the most recent forward (bench/diagnostics)
+STATS = {"forwards": 0, "hinted": 0, "overflow_retries": 0}
+DEBUG_CAPTURE = None    # tests set this to a dict: the next forward leaves its binning workspaces in it
 
 
-def _sink_of(t):
-    if t is None or not torch.is_tensor(t) or t.numel() == 0 or not grad_sinks:
+class GradSink:
+    """Destination of one leaf tensor's gradient inside a flat bucket (dist.GradBucket): when a leaf carries
+    one (attribute `_gg_sink` on the tensor OBJECT -- never keyed by address, so a recycled allocation cannot
+    alias it), backward writes that input's gradient straight into the bucket and autograd adopts the view as
+    `.grad` without a copy.  A sink is used at most ONCE per arming (GradBucket.zero() arms it) and only while
+    `leaf.grad is None`: every further backward before the next zero() returns a fresh tensor, which autograd
+    accumulates into the adopted view -- so gradient accumulation over several backward() calls stays exact."""
+
+    __slots__ = ("flat", "offset", "shape", "armed")
+
+    def __init__(self, flat, offset, shape):
+        self.flat, self.offset, self.shape, self.armed = flat, int(offset), tuple(shape), False
+
+
+def _sink_ref(t):
+    """weakref to an input that carries a usable sink (None otherwise)."""
+    if t is None or not torch.is_tensor(t) or t.numel() == 0:
         return None
-    ent = grad_sinks.get(t.data_ptr())
-    if ent is None or tuple(t.shape) != ent[2] or not t.is_contiguous():
+    ent = getattr(t, "_gg_sink", None)
+    if ent is None or tuple(t.shape) != ent.shape or not t.is_contiguous() or not t.is_leaf:
         return None
-    return ent
+    return weakref.ref(t)
+
+
+# Instance-capacity hints: (device, N, W, H) -> [capacity, largest per-tile count].  With a hint the forward is
+# enqueued WITHOUT waiting for num_rendered (upstream blocks on a D2H copy in the middle of every forward,
+# SURVEY.md 3.1); K is read once everything is queued and the rare overflow re-runs the instance stages.
+_hints = {}
+
+
+def _capacity_for(K: int) -> int:
+    return int(K * 1.25) + 4096
 
 
 def _pinned_word(device_index: int) -> torch.Tensor:
@@ -149,8 +173,22 @@ class _RasterizeGaussians(torch.autograd.Function):
                 _capi.check(lib.gg_forward_workspace_bytes(C.byref(view), C.byref(gb), C.byref(tb), C.byref(ib)),
                             "gg_forward_workspace_bytes")
                 geom_ws, tile_ws, image_ws = _ws(gb.value, dev), _ws(tb.value, dev), _ws(ib.value, dev)
-                K, max_tile = 0, 0
+                K, max_tile, capacity = 0, 0, 0
+                key_ws = record_ws = None
+
+                def render(cap, mt):
+                    kb, rb = C.c_size_t(), C.c_size_t()
+                    _capi.check(lib.gg_instance_workspace_bytes(cap, C.byref(kb), C.byref(rb)),
+                                "gg_instance_workspace_bytes")
+                    kw, rw = _ws(kb.value, dev), _ws(rb.value, dev)
+                    _capi.check(lib.gg_forward_render(C.byref(view), C.byref(inputs), geom_ws.data_ptr(),
+                                                      tile_ws.data_ptr(), kw.data_ptr(), rw.data_ptr(), cap, mt,
+                                                      image_ws.data_ptr(), _ptr(radii), color.data_ptr(),
+                                                      depth.data_ptr(), alpha.data_ptr(), di, sp), "gg_forward_render")
+                    return kw, rw
+
                 if N > 0:
+                    STATS["forwards"] += 1
                     word = _pinned_word(di)
                     _capi.check(lib.gg_forward_project(C.byref(view), C.byref(inputs), geom_ws.data_ptr(),
                                                        tile_ws.data_ptr(), radii.data_ptr(), word.data_ptr(), di, sp),
@@ -159,16 +197,23 @@ class _RasterizeGaussians(torch.autograd.Function):
                     k_ready.record(stream)
                     _capi.check(lib.gg_forward_color(C.byref(view), C.byref(inputs), geom_ws.data_ptr(),
                                                      radii.data_ptr(), di, sp), "gg_forward_color")
-                    k_ready.synchronize()        # only the scan + 4-byte copy; the SH kernel keeps running
+                    hkey = (di, N, W, H)
+                    hint = None if s.debug else _hints.get(hkey)
+                    if hint is not None:
+                        # everything is enqueued before the host looks at K: the GPU never waits for the host
+                        STATS["hinted"] += 1
+                        capacity = hint[0]
+                        key_ws, record_ws = render(capacity, hint[1])
+                    k_ready.synchronize()        # scan + 8-byte copy only; later kernels keep running
                     K, max_tile = (int(v) & 0xFFFFFFFF for v in word.tolist())
-                kb, rb = C.c_size_t(), C.c_size_t()
-                _capi.check(lib.gg_instance_workspace_bytes(K, C.byref(kb), C.byref(rb)), "gg_instance_workspace_bytes")
-                key_ws, record_ws = _ws(kb.value, dev), _ws(rb.value, dev)
-                _capi.check(lib.gg_forward_render(C.byref(view), C.byref(inputs), geom_ws.data_ptr(), tile_ws.data_ptr(),
-                                                  key_ws.data_ptr(), record_ws.data_ptr(), K, max_tile,
-                                                  image_ws.data_ptr(),
-                                                  _ptr(radii), color.data_ptr(), depth.data_ptr(), alpha.data_ptr(),
-                                                  di, sp), "gg_forward_render")
+                    if hint is None or K > capacity:
+                        if hint is not None:
+                            STATS["overflow_retries"] += 1
+                        capacity = K
+                        key_ws, record_ws = render(capacity, max_tile)
+                    _hints[hkey] = [max(_capacity_for(K), int(0.9 * (hint[0] if hint else 0))), max_tile]
+                else:
+                    key_ws, record_ws = render(0, 0)
         except Exception:
             if s.debug:
                 torch.save(dict(means3D=means3D, sh=sh, colors_precomp=colors_precomp, opacities=opacities,
@@ -179,10 +224,14 @@ class _RasterizeGaussians(torch.autograd.Function):
 
         global LAST_NUM_RENDERED
         LAST_NUM_RENDERED = K
+        if DEBUG_CAPTURE is not None:
+            DEBUG_CAPTURE.update(view=view, tile_ws=tile_ws, record_ws=record_ws, capacity=capacity, K=K,
+                                 max_tile=max_tile, device=di)
         ctx.raster_settings = s
-        ctx.num_rendered = K
-        ctx.sinks = tuple(_sink_of(t) for t in (means3D, sh, colors_precomp, opacities, scales, rotations,
-                                                cov3Ds_precomp))
+        ctx.num_rendered = capacity          # record_ws was laid out for this many instances
+        ctx.set_materialize_grads(False)     # unused outputs (depth / alpha in the training loops) arrive as None
+        ctx.sinks = tuple(_sink_ref(t) for t in (means3D, sh, colors_precomp, opacities, scales, rotations,
+                                                 cov3Ds_precomp))
         ctx.shapes = (N, M)
         ctx.has = (shs is not None, col is not None, sc is not None, cv is not None)
         # NOTE: `color` is deliberately NOT saved: the reference's ssim() multiplies it in place before
@@ -220,19 +269,22 @@ class _RasterizeGaussians(torch.autograd.Function):
             return g.contiguous()
 
         gc, gd, ga = gprep(grad_color), gprep(grad_depth), gprep(grad_alpha)
+        if gc is not None and gc.data_ptr() % 16:
+            gc = gc.clone()
         view = _view_struct(s, N, M)
         inputs = GGInputs(_ptr(m3), _ptr(shs), _ptr(col), _ptr(op), _ptr(sc), _ptr(ro), _ptr(cv),
                           _ptr(bg), _ptr(vm), _ptr(pm), _ptr(cp))
         sinks = ctx.sinks
 
         def E(slot, *shape):
-            ent = sinks[slot] if slot is not None else None
-            if ent is not None and ent[2] == tuple(shape):
-                flat, off, _ = ent
+            leaf = sinks[slot]() if (slot is not None and sinks[slot] is not None) else None
+            ent = getattr(leaf, "_gg_sink", None) if leaf is not None else None
+            if ent is not None and ent.armed and leaf.grad is None and ent.shape == tuple(shape):
+                ent.armed = False                            # at most one zero-copy hand-off per arming
                 n = 1
                 for d in shape:
                     n *= d
-                return flat[off:off + n].view(*shape)        # fresh view: autograd adopts it as .grad
+                return ent.flat[ent.offset:ent.offset + n].view(*shape)    # fresh view: autograd adopts it as .grad
             return torch.empty(*shape, dtype=torch.float32, device=dev)
 
         g_m3 = E(0, N, 3) if need[0] else None
@@ -248,7 +300,7 @@ class _RasterizeGaussians(torch.autograd.Function):
                 sp = torch.cuda.current_stream(dev).cuda_stream
                 ab = C.c_size_t()
                 _capi.check(lib.gg_backward_workspace_bytes(C.byref(view), C.byref(ab)), "gg_backward_workspace_bytes")
-                accum_ws = _ws(ab.value, dev, zero=True)
+                accum_ws = _ws(ab.value, dev)         # zero-filled by gg_backward itself
                 _capi.check(lib.gg_backward(C.byref(view), C.byref(inputs), tile_ws.data_ptr(), record_ws.data_ptr(),
                                             ctx.num_rendered, image_ws.data_ptr(), radii.data_ptr(), accum_ws.data_ptr(),
                                             _ptr(gc), _ptr(gd), _ptr(ga), _ptr(g_m3), _ptr(g_m2), _ptr(g_sh),

@@ -79,7 +79,7 @@ int gg_forward_workspace_bytes(const gg_view* view, size_t* geom_bytes, size_t* 
 /* keys: transient (tile-bucketed depth keys); records: packed sorted per-instance records,
  * needed again by backward.  `num_rendered` = K.                                          */
 int gg_instance_workspace_bytes(int64_t num_rendered, size_t* key_bytes, size_t* record_bytes);
-/* per-Gaussian gradient accumulators, transient within backward (must be zero-filled).  */
+/* per-Gaussian gradient accumulators, transient within backward (gg_backward zero-fills them). */
 int gg_backward_workspace_bytes(const gg_view* view, size_t* accum_bytes);
 
 /* ---- forward, stage 1a: replaces the first half of `_C.rasterize_gaussians`
@@ -115,7 +115,7 @@ int gg_forward_render(const gg_view* view, const gg_inputs* in, const void* geom
  * zeros).  Output gradients (any may be NULL = not wanted): dL_dmeans3D[N,3],
  * dL_dmeans2D[N,3] (side channel, z = 0; consumer scene/gaussian_model.py:410-412),
  * dL_dshs[N,M,3], dL_dcolors_precomp[N,3], dL_dopacities[N,1], dL_dscales[N,3],
- * dL_drotations[N,4], dL_dcov3D[N,6].  accum_ws must be zero-filled on entry;
+ * dL_drotations[N,4], dL_dcov3D[N,6].  accum_ws is scratch (zero-filled here);
  * `instance_capacity` must be the value given to gg_forward_render for `record_ws`.      */
 int gg_backward(const gg_view* view, const gg_inputs* in, const void* tile_ws, const void* record_ws,
                 int64_t instance_capacity, const void* image_ws, const int32_t* radii, void* accum_ws,
@@ -172,6 +172,13 @@ int gg_photometric_backward(int32_t width, int32_t height, const float* image, c
  * x0 | y0<<16, x1 | y1<<16); any may be NULL.                                             */
 int gg_debug_read_geom(const gg_view* view, const void* geom_ws, float* xy, float* depth,
                        float* conic_opacity, float* rgb, uint32_t* rect, int device, void* stream);
+/* copies the binning result out for index-level parity tests (rows a6-a8): tile_offsets[T+1] (uint32, exclusive
+ * scan of the per-tile instance counts; tile_offsets[T] = K) and, for the full-sort forward path, the Gaussian id of
+ * every sorted instance sorted_ids[instance_capacity] (uint32; entries of tile t are
+ * sorted_ids[tile_offsets[t] .. tile_offsets[t+1]) in front-to-back order).  Either output may be NULL; device or
+ * host destinations.                                                                        */
+int gg_debug_read_binning(const gg_view* view, const void* tile_ws, const void* record_ws, int64_t instance_capacity,
+                          uint32_t* tile_offsets, uint32_t* sorted_ids, int device, void* stream);
 /* number of kernels this library launched (process-wide: backward runs on an autograd worker
  * thread) since the last reset.                                                            */
 int64_t gg_launch_count(int reset);

@@ -24,3 +24,17 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """Measured parity numbers (fragile-pixel counts, per-tensor and per-element gradient errors) -> gpurun_out/."""
+    try:
+        import json
+        import helpers
+        if helpers.REPORT:
+            out = os.path.join(ROOT, "gpurun_out")
+            os.makedirs(out, exist_ok=True)
+            with open(os.path.join(out, "parity_report.json"), "w") as f:
+                json.dump(helpers.REPORT, f, indent=1)
+    except Exception:
+        pass

@@ -75,10 +75,37 @@ def rel_inf(a, b):
     return float((a.float() - b.float()).abs().max() / b.float().abs().max().clamp_min(1e-12))
 
 
+REPORT = {}     # test name -> measured numbers; dumped to gpurun_out/parity_report.json at session end (conftest.py)
+
+
+def _note(key, **kv):
+    name = os.environ.get("PYTEST_CURRENT_TEST", "?").split(" ")[0]
+    REPORT.setdefault(name, {}).setdefault(key, {}).update(kv)
+
+
+def fragile_bound(ref, tol):
+    """What a pixel the oracle flags as sitting on a discrete threshold may differ by: tol + ONE contributor whose
+    keep/drop decision flips.  Such a contributor has alpha ~ 1/255 (its weight alpha*T <= (1/255 + eps)) or is the
+    one that ends the pixel (everything behind it weighs < T_STOP-ish * alpha_max); the colour it moves is bounded
+    by the largest Gaussian colour / depth in the scene.  Factor 1.5: an alpha flip also rescales what lies behind."""
+    ctx = ref.get("ctx")
+    cmax, dmax = 1.0, 1.0
+    if ctx is not None:
+        g = ctx.geom()
+        vis = ref["radii"] > 0
+        if bool(vis.any()):
+            cmax = max(1.0, float(g["rgb"][vis].abs().max()))
+            dmax = max(1.0, float(g["depth"][vis].abs().max()))
+    w = 1.5 * (1.0 / 255.0 + 2e-4)
+    return {"color": tol + w * cmax, "alpha": tol + w, "depth": tol * dmax + w * dmax}
+
+
 def assert_images_close(got, ref, tol=RGB_TOL, max_fragile_frac=1e-2):
-    """All pixels within tol except those the oracle flags as sitting on a discrete threshold
-    (alpha ~ 1/255 or T ~ 1e-4), which must stay a tiny fraction."""
+    """All pixels within tol, except those the oracle flags as sitting on a discrete threshold (alpha ~ 1/255 or
+    T ~ 1e-4): those must stay a small fraction AND within fragile_bound() (one flipped contributor)."""
     frag = ref["fragile"]
+    fb = fragile_bound(ref, tol)
+    stats = {}
     for name, t in (("color", tol), ("alpha", tol), ("depth", None)):
         d = (got[name] - ref[name]).abs()
         if name == "depth":   # un-normalised depth carries the scene scale: relative tolerance
@@ -89,10 +116,38 @@ def assert_images_close(got, ref, tol=RGB_TOL, max_fragile_frac=1e-2):
         assert int(unexplained.sum()) == 0, (
             f"{name}: {int(unexplained.sum())} pixels differ by more than {t} (max {float(d.max()):.3e}) "
             f"away from discrete thresholds")
-    assert float(frag.float().mean()) <= max_fragile_frac or int(frag.sum()) < 64
+        worst_frag = float(d[frag].max()) if bool(frag.any()) else 0.0
+        assert worst_frag <= fb[name], (
+            f"{name}: a threshold pixel differs by {worst_frag:.3e} > bound {fb[name]:.3e} (one flipped contributor)")
+        stats[name] = dict(max_err_regular=float(d[~frag].max()) if bool((~frag).any()) else 0.0,
+                           max_err_fragile=worst_frag, fragile_over_tol=int((bad & frag).sum()))
+    n_frag = int(frag.sum())
+    stats["fragile_pixels"] = n_frag
+    stats["fragile_frac"] = float(frag.float().mean())
+    _note("images", **stats)
+    print(f"[parity] fragile pixels: {n_frag} ({100 * stats['fragile_frac']:.3f} %), of which over tol: "
+          f"{stats['color']['fragile_over_tol']} colour / {stats['alpha']['fragile_over_tol']} alpha; "
+          f"worst fragile colour err {stats['color']['max_err_fragile']:.2e} (bound {fb['color']:.2e})")
+    assert float(frag.float().mean()) <= max_fragile_frac or n_frag < 64
 
 
-def assert_grads_close(got, ref, tol=GRAD_TOL):
+def elementwise_rel(g, g_ref, floor=1e-6):
+    """per-element relative error on entries whose reference magnitude exceeds `floor`."""
+    g, g_ref = g.float().reshape(-1), g_ref.float().reshape(-1)
+    sel = g_ref.abs() > floor
+    if not bool(sel.any()):
+        return None
+    e = ((g[sel] - g_ref[sel]).abs() / g_ref[sel].abs()).sort().values
+    n = e.numel()
+    q = lambda f: float(e[min(n - 1, int(f * n))])
+    return dict(n=int(n), p50=q(0.5), p90=q(0.9), p99=q(0.99), p999=q(0.999), max=float(e[-1]))
+
+
+def assert_grads_close(got, ref, tol=GRAD_TOL, elem_p50=1e-4, elem_p99=1e-2):
+    """(1) tensor-level: ||g - g_ref||_inf / ||g_ref||_inf <= tol (north_star: 1e-3).
+    (2) element-level: relative error of every entry with |g_ref| > 1e-6; fp32 sums with
+    cancellation cannot hold 1e-3 on every small entry, so the distribution is bounded (median, 99th percentile)
+    and recorded in the parity report."""
     for name, g_ref in ref.items():
         if g_ref is None:
             continue
@@ -101,4 +156,25 @@ def assert_grads_close(got, ref, tol=GRAD_TOL):
         assert g.shape == g_ref.shape, (name, g.shape, g_ref.shape)
         assert torch.isfinite(g).all(), f"non-finite gradient {name}"
         err = rel_inf(g, g_ref)
+        st = elementwise_rel(g, g_ref)
+        _note("grads", **{name: dict(rel_inf=err, elementwise=st)})
         assert err <= tol, f"grad {name}: rel-inf error {err:.3e} > {tol}"
+        if st is not None and st["n"] >= 100:
+            assert st["p50"] <= elem_p50, f"grad {name}: median per-element rel. error {st['p50']:.2e} > {elem_p50}"
+            assert st["p99"] <= elem_p99, f"grad {name}: 99th pct per-element rel. error {st['p99']:.2e} > {elem_p99}"
+
+
+def worst_gaussians(got, ref, name, k=5):
+    """ids of the Gaussians whose gradient `name` deviates most (diagnostics for a failing tolerance)."""
+    d = (got[name].float() - ref[name].float()).abs().reshape(ref[name].shape[0], -1).amax(1)
+    idx = torch.topk(d, min(k, d.numel())).indices
+    scale = float(ref[name].abs().max().clamp_min(1e-12))
+    return [(int(i), float(d[i]) / scale) for i in idx]
+
+
+def mask_upstream(grads, fragile):
+    """Zero the upstream gradients on the pixels the oracle flags as sitting on a discrete threshold, for BOTH
+    implementations: a keep/drop decision that legitimately differs between ex2.approx and expf then cannot leak
+    into the comparison, and no tolerance has to be widened."""
+    keep = (~fragile).float()[None]
+    return tuple(None if g is None else g * keep for g in grads)

@@ -103,14 +103,24 @@ def test_bucket_adopt_copies_foreign_grads_and_zero_fills_missing():
 
 
 def test_grad_sink_registry_roundtrip():
+    """Sinks live on the tensor OBJECT (never keyed by address: ADVICE r1), are usable once per arming and only
+    for leaves, and disappear with unregister()."""
     from gaussian_garments_b200 import rasterizer
     params = [torch.zeros(4, 3, requires_grad=True)]
     b = GradBucket(params, 1)
     try:
-        ent = rasterizer._sink_of(params[0])
-        assert ent is not None and ent[0] is b.flat and ent[2] == (4, 3)
-        assert rasterizer._sink_of(torch.zeros(4, 3)) is None          # unknown tensor: no sink
-        assert rasterizer._sink_of(params[0][:2]) is None or rasterizer._sink_of(params[0][:2])[2] != (2, 3)
+        ref = rasterizer._sink_ref(params[0])
+        assert ref is not None and ref() is params[0]
+        ent = params[0]._gg_sink
+        assert ent.flat is b.flat and ent.shape == (4, 3) and ent.armed is False
+        b.zero()
+        assert ent.armed is True
+        assert rasterizer._sink_ref(torch.zeros(4, 3, requires_grad=True)) is None      # unknown tensor: no sink
+        assert rasterizer._sink_ref(params[0][:2]) is None                              # a view is not the leaf
+        # a new tensor that happens to reuse the parameter's storage address must not inherit the sink
+        alias = torch.zeros(4, 3, requires_grad=True)
+        alias.data = params[0].data
+        assert alias.data_ptr() == params[0].data_ptr() and rasterizer._sink_ref(alias) is None
     finally:
         b.unregister()
-    assert rasterizer._sink_of(params[0]) is None
+    assert rasterizer._sink_ref(params[0]) is None
