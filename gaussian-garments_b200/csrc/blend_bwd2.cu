@@ -36,7 +36,8 @@ struct B2Smem {
     float4 s0[B2_STAGES][B2_BATCH];
     float4 s1[B2_STAGES][B2_BATCH];
     float4 s2[B2_STAGES][B2_BATCH];
-    float4 gpix[B2_WARPS][32];                      // (gC0, gC1, gC2, gD) of the warp's 32 pixels
+    float4 gpix[B2_WARPS][2][17];                   // (gC0, gC1, gC2, gD) of the warp's 2 x 16 pixels; the odd pitch keeps
+                                                    // the two half-warp broadcast reads of phase 2 on different banks
     float4 meta[B2_WARPS][B2_ROUND][2];             // (mx, my, A', B') , (C', opacity, depth, id bits)
     float2 xw[B2_WARPS][B2_ROUND * B2_PITCH];       // (X, w) panel: [entry][pixel], row pitch 33 -> conflict-free
     uint64_t full[B2_STAGES];
@@ -49,7 +50,7 @@ constexpr uint32_t O_S0 = offsetof(B2Smem, s0), O_S1 = offsetof(B2Smem, s1), O_S
 constexpr uint32_t O_GPIX = offsetof(B2Smem, gpix), O_META = offsetof(B2Smem, meta), O_XW = offsetof(B2Smem, xw);
 constexpr uint32_t O_FULL = offsetof(B2Smem, full), O_EMPTY = offsetof(B2Smem, empty), O_SMAX = offsetof(B2Smem, s_max);
 constexpr uint32_t STAGE_BYTES = B2_BATCH * 16;
-constexpr uint32_t XW_WARP_BYTES = B2_ROUND * B2_PITCH * 8, META_WARP_BYTES = B2_ROUND * 32, GPIX_WARP_BYTES = 32 * 16;
+constexpr uint32_t XW_WARP_BYTES = B2_ROUND * B2_PITCH * 8, META_WARP_BYTES = B2_ROUND * 32, GPIX_WARP_BYTES = 2 * 17 * 16;
 
 __device__ __forceinline__ void mbar_init_a(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -117,7 +118,7 @@ __device__ __forceinline__ void b2_flush(int cnt, uint32_t sb, int W, int H, int
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int e = lane & (B2_ROUND - 1), h = lane >> 4;
     const uint32_t row = sb + O_XW + (uint32_t)warp * XW_WARP_BYTES + 8u * (uint32_t)(e * B2_PITCH + h * 16);
-    const uint32_t gp = sb + O_GPIX + (uint32_t)warp * GPIX_WARP_BYTES + 256u * (uint32_t)h;
+    const uint32_t gp = sb + O_GPIX + (uint32_t)warp * GPIX_WARP_BYTES + 272u * (uint32_t)h;
     float A0 = 0.f, B0 = 0.f, C0 = 0.f, A1 = 0.f, B1 = 0.f, C1 = 0.f;
     float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
 #pragma unroll
@@ -162,11 +163,12 @@ __device__ __forceinline__ void b2_flush(int cnt, uint32_t sb, int W, int H, int
     if (DA) q3 += __shfl_xor_sync(FULL, q3, 16);
     if (e < cnt) {
         const uint32_t id = __float_as_uint(m1.w);
+        // every parked entry had at least one contributing pixel (phase 1's vote): no zero tests needed
         if (h == 0) {
-            if (v0 != 0.f || v1 != 0.f || v2 != 0.f || v3 != 0.f) atomicAdd(&a0[id], make_float4(v0, v1, v2, v3));
-            if (q2 != 0.f || q3 != 0.f) atomicAdd(&a2[id], make_float2(q2, q3));
+            atomicAdd(&a0[id], make_float4(v0, v1, v2, v3));
+            atomicAdd(&a2[id], make_float2(q2, q3));
         } else {
-            if (v4 != 0.f || v5 != 0.f || q0 != 0.f || q1 != 0.f) atomicAdd(&a1[id], make_float4(v4, v5, q0, q1));
+            atomicAdd(&a1[id], make_float4(v4, v5, q0, q1));
         }
     }
 }
@@ -220,7 +222,8 @@ blend_bwd2_kernel(const uint32_t* __restrict__ tile_offset, const float4* __rest
         if (DA && dL_ddepth) gD = dL_ddepth[pid];
         if (DA && dL_dalpha) gA = dL_dalpha[pid];
     }
-    sts128(sb + O_GPIX + (uint32_t)warp * GPIX_WARP_BYTES + 16u * lane, make_float4(gC0, gC1, gC2, gD));
+    sts128(sb + O_GPIX + (uint32_t)warp * GPIX_WARP_BYTES + 272u * (uint32_t)(lane >> 4) + 16u * (lane & 15),
+           make_float4(gC0, gC1, gC2, gD));
     __syncwarp();
     float R = T_final * (bg[0] * gC0 + bg[1] * gC1 + bg[2] * gC2);     // suffix sum, starts with the background term
     const float fx = (float)px, fy = (float)py;

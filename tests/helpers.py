@@ -143,11 +143,12 @@ def elementwise_rel(g, g_ref, floor=1e-6):
     return dict(n=int(n), p50=q(0.5), p90=q(0.9), p99=q(0.99), p999=q(0.999), max=float(e[-1]))
 
 
-def assert_grads_close(got, ref, tol=GRAD_TOL, elem_p50=1e-4, elem_p99=1e-2):
+def assert_grads_close(got, ref, tol=GRAD_TOL, elem_p50=2e-5, elem_p99=1e-3):
     """(1) tensor-level: ||g - g_ref||_inf / ||g_ref||_inf <= tol (north_star: 1e-3).
     (2) element-level: relative error of every entry with |g_ref| > 1e-6; fp32 sums with
-    cancellation cannot hold 1e-3 on every small entry, so the distribution is bounded (median, 99th percentile)
-    and recorded in the parity report."""
+    cancellation cannot hold 1e-3 on every small entry (measured on the B200: median ~5e-7, 99th percentile
+    <= 1.4e-4, 99.9th ~3e-3, isolated entries O(1) where the reference value is a cancelled sum ~1e-6), so the
+    distribution is bounded -- median <= 2e-5, 99 % of the entries within 1e-3 -- and recorded in the parity report."""
     for name, g_ref in ref.items():
         if g_ref is None:
             continue

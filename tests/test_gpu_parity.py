@@ -771,3 +771,117 @@ def test_hinted_forward_equals_synchronous_forward_and_recovers_from_overflow():
         assert torch.equal(a[k], c[k])
     for k in ("means3D", "shs", "opacities", "scales", "rotations"):
         assert h.rel_inf(c["grads"][k], a["grads"][k]) < 1e-4
+
+
+# ------------------------------------------------------------------------------------ the reference facade, replayed
+def _facade_inputs(sc, z, dev):
+    """Rebuild on the GPU what /root/reference/gaussian_renderer/__init__.py hands to the rasterizer in scenario `sc`
+    (the trace was recorded from the unmodified facade: tests/golden/make_facade_trace.py)."""
+    T = lambda k: torch.tensor(z[k]).to(dev)
+    grad_mode = sc["fn"] == "render"
+    leaf = (lambda t: t.clone().requires_grad_(True)) if grad_mode else (lambda t: t)
+    xyz, log_s, rot, shs = leaf(T("means3D")), leaf(torch.log(T("scales"))), leaf(T("rotations")), leaf(T("shs"))
+    logit_o = leaf(torch.logit(T("opacities").clamp(1e-4, 1 - 1e-4)))
+    opt = sc["options"]
+    with torch.set_grad_enabled(grad_mode):
+        screenspace = torch.zeros_like(xyz, requires_grad=True) + 0                       # facade :29 / :132
+        if grad_mode:
+            screenspace.retain_grad()
+        means3D = (xyz + 0.01) * 1.0 + 0.5 if opt.get("avatar") else xyz                  # get_final_xyz vs get_xyz (:56)
+        kw = dict(means3D=means3D, means2D=screenspace, opacities=torch.sigmoid(logit_o), shs=None, colors_precomp=None,
+                  scales=None, rotations=None, cov3D_precomp=None)
+        if sc["pipe"]["compute_cov3D_python"]:
+            kw["cov3D_precomp"] = T(f"{sc['name']}__cov3D_precomp")                       # computed by the reference (:70)
+            if grad_mode:
+                kw["cov3D_precomp"] = kw["cov3D_precomp"] + 0 * log_s.sum()               # non-leaf, requires grad
+        else:
+            kw["scales"], kw["rotations"] = torch.exp(log_s), torch.nn.functional.normalize(rot)
+        if opt.get("override_color"):
+            kw["colors_precomp"] = T("override_color")
+        elif sc["pipe"]["convert_SHs_python"]:
+            kw["colors_precomp"] = T(f"{sc['name']}__colors_precomp") + 0 * shs.sum()    # eval_sh by the reference (:81-85)
+        elif opt.get("override_shs"):
+            kw["shs"] = T("override_shs")
+        else:
+            kw["shs"] = shs * 1.5 if opt.get("avatar") else shs                           # pc.shs vs get_features (:87)
+        if opt.get("vis_mask"):
+            m = T("vis_mask")
+            kw = {k: (v[m] if v is not None else None) for k, v in kw.items()}           # :92-100
+    return kw, screenspace, dict(xyz=xyz, log_s=log_s, rot=rot, shs=shs, logit_o=logit_o)
+
+
+def test_reference_facade_trace_replay():
+    """Rows a1/a2: every call the reference's render() / doll_render() makes (recorded from the unmodified facade with a
+    recording rasterizer) goes through THIS package with the same keywords, dtypes, shapes, strides and autograd
+    structure, and what comes back satisfies the facade's return contract (gaussian_renderer/__init__.py:115-122, :221)."""
+    import json, os
+    import numpy as np
+    here = os.path.dirname(os.path.abspath(__file__))
+    trace = json.load(open(os.path.join(here, "golden", "facade_trace.json")))
+    z = np.load(os.path.join(here, "golden", "facade_trace.npz"))
+    dev = torch.device("cuda:0")
+    cam = gg.scenes.cfg1_camera(trace["W"], trace["H"]).to(dev)
+    N, H, W = trace["N"], trace["H"], trace["W"]
+    bg = torch.tensor(z["bg"]).to(dev)
+    images = {}
+    for sc in trace["scenarios"]:
+        kw, screenspace, leaves = _facade_inputs(sc, z, dev)
+        # the inputs we rebuilt are what the facade passed: same None pattern, shapes, dtypes, strides, autograd flags
+        for k, meta in sc["call"].items():
+            if meta is None:
+                assert kw[k] is None, (sc["name"], k)
+                continue
+            t = kw[k]
+            assert list(t.shape) == meta["shape"] and str(t.dtype) == "torch." + meta["dtype"], (sc["name"], k)
+            assert list(t.stride()) == meta["stride"] and t.requires_grad == meta["requires_grad"], (sc["name"], k)
+        # settings: exactly the recorded keyword set, scalars as recorded, tensors from the camera / state
+        sk = dict(sc["settings_scalars"])
+        assert abs(sk["tanfovx"] - cam.tanfovx) < 1e-12 and abs(sk["tanfovy"] - cam.tanfovy) < 1e-12
+        sk.update(bg=bg, viewmatrix=cam.world_view_transform, projmatrix=cam.full_proj_transform,
+                  campos=cam.camera_center)
+        settings = h.dgr.GaussianRasterizationSettings(**{k: sk[k] for k in sc["settings_keys"]})
+        rasterizer = h.dgr.GaussianRasterizer(raster_settings=settings)
+        with torch.set_grad_enabled(sc["fn"] == "render"):
+            out = rasterizer(**{k: kw[k] for k in sc["call_keys"]})
+        assert isinstance(out, tuple) and len(out) == 4
+        rendered_image, radii, depth, alpha = out
+        images[sc["name"]] = rendered_image.detach().clone()
+        n_call = sc["call"]["means3D"]["shape"][0]
+        assert rendered_image.shape == (3, H, W) and depth.shape == (1, H, W) and alpha.shape == (1, H, W)
+        assert radii.shape == (n_call,) and radii.dtype == torch.int32 and not radii.requires_grad
+        vis = radii > 0                                                               # "visibility_filter" (:118)
+        assert vis.dtype == torch.bool and 0 < int(vis.sum()) <= n_call
+        assert torch.isfinite(rendered_image).all() and float(alpha.max()) <= 1.0 + 1e-5
+        if sc["fn"] == "render":
+            assert rendered_image.requires_grad
+            gt = torch.rand_like(rendered_image)
+            loss = (rendered_image - gt).abs().mean()
+            rendered_image *= (torch.rand(1, H, W, device=dev) > 0.2).float()           # ssim(): in-place mask (loss_utils.py:45)
+            (loss + rendered_image.mean()).backward()
+            g = screenspace.grad                                                       # "viewspace_points" (:116, gaussian_model.py:411)
+            assert list(g.shape) == sc["returns"]["viewspace_points_grad_shape"] == [N, 3]
+            assert float(g[:, 2].abs().max()) == 0.0 and float(g[:, :2].abs().max()) > 0
+            if sc["options"].get("vis_mask"):
+                assert float(g[~torch.tensor(z["vis_mask"]).to(dev)].abs().max()) == 0.0
+            assert leaves["xyz"].grad is not None and torch.isfinite(leaves["xyz"].grad).all()
+            assert float(leaves["logit_o"].grad.abs().max()) > 0
+            if sc["call"]["shs"] is not None:
+                assert float(leaves["shs"].grad.abs().max()) > 0
+            if sc["call"]["scales"] is not None:
+                assert float(leaves["log_s"].grad.abs().max()) > 0 and float(leaves["rot"].grad.abs().max()) > 0
+        else:
+            assert not rendered_image.requires_grad                                     # inference.py:462 no_grad
+            assert sc["returns"]["order"] == ["rendered_image", "depth", "alpha"]
+    # facade branches that must agree pixel for pixel (north_star: 1e-4):
+    #  SHs evaluated by the reference's own eval_sh (--convert_SHs_python, :81-85)  ==  SHs evaluated in-kernel
+    assert float((images["render_convert_SHs_python"] - images["render_default"]).abs().max()) < 1e-4
+    assert float((images["doll_default"] - images["render_default"]).abs().max()) == 0.0
+    #  covariance built by the reference's build_scaling_rotation (--compute_cov3D_python, modifier 1.3, :70) == in-kernel
+    kw, _, _ = _facade_inputs(trace["scenarios"][0], z, dev)
+    sk = h.settings_for(cam, gg.scenes.random_cloud(N, seed=5).to(dev), device=dev, scale_modifier=1.3)._replace(bg=bg)
+    with torch.no_grad():
+        ref_img, *_ = h.dgr.GaussianRasterizer(raster_settings=sk)(
+            means3D=kw["means3D"].detach(), means2D=torch.zeros_like(kw["means3D"]), shs=kw["shs"].detach(),
+            colors_precomp=None, opacities=kw["opacities"].detach(), scales=kw["scales"].detach(),
+            rotations=kw["rotations"].detach(), cov3D_precomp=None)
+    assert float((images["render_compute_cov3D_python"] - ref_img).abs().max()) < 1e-4
