@@ -118,6 +118,8 @@ def load():
         lib.gg_mesh_bind_workspace_bytes.argtypes = [C.c_int32, P(sz)]
         lib.gg_mesh_bind_forward.argtypes = [C.c_int32] * 3 + [vp] * 10 + [i32, vp]
         lib.gg_mesh_bind_backward.argtypes = [C.c_int32] * 3 + [vp] * 15 + [i32, vp]
+        lib.gg_mesh_bind_forward_ex.argtypes = [C.c_int32] * 3 + [vp] * 12 + [i32, vp]
+        lib.gg_mesh_bind_backward_ex.argtypes = [C.c_int32] * 3 + [vp] * 17 + [i32, vp]
         lib.gg_photometric_workspace_bytes.argtypes = [C.c_int32, C.c_int32, P(sz)]
         lib.gg_photometric_forward.argtypes = [C.c_int32, C.c_int32, vp, vp, vp, vp, C.c_int32, i32, vp]
         lib.gg_photometric_backward.argtypes = [C.c_int32, C.c_int32, vp, vp, vp, vp, C.c_float, C.c_float, vp, vp, i32, vp]
@@ -130,6 +132,7 @@ def load():
                      "gg_forward_project", "gg_forward_color", "gg_forward_render", "gg_backward",
                      "gg_mark_visible", "gg_debug_read_geom", "gg_debug_read_binning", "gg_kernel_timing", "gg_kernel_times",
                      "gg_mesh_bind_workspace_bytes", "gg_mesh_bind_forward", "gg_mesh_bind_backward",
+                     "gg_mesh_bind_forward_ex", "gg_mesh_bind_backward_ex",
                      "gg_photometric_workspace_bytes", "gg_photometric_forward", "gg_photometric_backward"):
             getattr(lib, name).restype = C.c_int
         if lib.gg_abi_version() != 1:
@@ -150,7 +153,7 @@ EXPORTED_SYMBOLS = [
     "gg_forward_render", "gg_backward", "gg_mark_visible", "gg_debug_read_geom", "gg_debug_read_binning",
     "gg_kernel_timing",
     "gg_kernel_count", "gg_kernel_name", "gg_kernel_times", "gg_mesh_bind_workspace_bytes", "gg_mesh_bind_forward",
-    "gg_mesh_bind_backward", "gg_photometric_workspace_bytes", "gg_photometric_forward", "gg_photometric_backward",
+    "gg_mesh_bind_backward", "gg_mesh_bind_forward_ex", "gg_mesh_bind_backward_ex", "gg_photometric_workspace_bytes", "gg_photometric_forward", "gg_photometric_backward",
 ]
 
 

@@ -370,10 +370,11 @@ int gg_mesh_bind_workspace_bytes(int32_t num_faces, size_t* frame_bytes) {
     return 0;
 }
 
-int gg_mesh_bind_forward(int32_t num_vertices, int32_t num_faces, int32_t num_gaussians, const float* verts,
-                         const int32_t* faces, const int32_t* binding, const float* local_xyz,
-                         const float* local_log_scaling, const float* local_rotation, void* frame_ws, float* out_xyz,
-                         float* out_scaling, float* out_rotation, int device, void* stream) {
+int gg_mesh_bind_forward_ex(int32_t num_vertices, int32_t num_faces, int32_t num_gaussians, const float* verts,
+                            const int32_t* faces, const int32_t* binding, const float* local_xyz,
+                            const float* local_log_scaling, const float* local_rotation, const float* barycentric,
+                            const float* face_scaling_remembered, void* frame_ws, float* out_xyz, float* out_scaling,
+                            float* out_rotation, int device, void* stream) {
     (void)num_vertices;
     if (num_faces < 0 || num_gaussians < 0) return fail(GG_E_BADARG, "negative size");
     if (num_gaussians > 0 && (!verts || !faces || !binding || !local_xyz || !local_log_scaling || !local_rotation ||
@@ -386,20 +387,37 @@ int gg_mesh_bind_forward(int32_t num_vertices, int32_t num_faces, int32_t num_ga
     {
         ScopedKernelTimer kt(K_MESHFWD, s);
         g_launches += launch_mesh_bind_forward(num_faces, num_gaussians, verts, faces, binding, local_xyz, local_log_scaling,
-                                               local_rotation, (float*)frame_ws, out_xyz, out_scaling, out_rotation, s);
+                                               local_rotation, barycentric, face_scaling_remembered, (float*)frame_ws,
+                                               out_xyz, out_scaling, out_rotation, s);
     }
     GG_AFTER("mesh_bind_forward");
     return 0;
 }
 
-int gg_mesh_bind_backward(int32_t num_vertices, int32_t num_faces, int32_t num_gaussians, const float* verts,
-                          const int32_t* faces, const int32_t* binding, const float* local_xyz,
-                          const float* local_log_scaling, const float* local_rotation, const void* frame_ws,
-                          void* frame_grad_ws, const float* dL_dxyz, const float* dL_dscaling, const float* dL_drotation,
-                          float* dL_dverts, float* dL_dlocal_xyz, float* dL_dlocal_log_scaling, float* dL_dlocal_rotation,
-                          int device, void* stream) {
+int gg_mesh_bind_forward(int32_t num_vertices, int32_t num_faces, int32_t num_gaussians, const float* verts,
+                         const int32_t* faces, const int32_t* binding, const float* local_xyz,
+                         const float* local_log_scaling, const float* local_rotation, void* frame_ws, float* out_xyz,
+                         float* out_scaling, float* out_rotation, int device, void* stream) {
+    return gg_mesh_bind_forward_ex(num_vertices, num_faces, num_gaussians, verts, faces, binding, local_xyz,
+                                   local_log_scaling, local_rotation, nullptr, nullptr, frame_ws, out_xyz, out_scaling,
+                                   out_rotation, device, stream);
+}
+
+int gg_mesh_bind_backward_ex(int32_t num_vertices, int32_t num_faces, int32_t num_gaussians, const float* verts,
+                             const int32_t* faces, const int32_t* binding, const float* local_xyz,
+                             const float* local_log_scaling, const float* local_rotation, const float* barycentric,
+                             const float* face_scaling_remembered, const void* frame_ws, void* frame_grad_ws,
+                             const float* dL_dxyz, const float* dL_dscaling, const float* dL_drotation, float* dL_dverts,
+                             float* dL_dlocal_xyz, float* dL_dlocal_log_scaling, float* dL_dlocal_rotation, int device,
+                             void* stream) {
     if (num_vertices < 0 || num_faces < 0 || num_gaussians < 0) return fail(GG_E_BADARG, "negative size");
-    if (num_gaussians == 0) return 0;
+    if (num_gaussians == 0) {
+        if (dL_dverts && num_vertices > 0) {
+            GG_CUDA(cudaSetDevice(device));
+            GG_CUDA(cudaMemsetAsync(dL_dverts, 0, (size_t)num_vertices * 3 * sizeof(float), (cudaStream_t)stream));
+        }
+        return 0;
+    }
     if (!verts || !faces || !binding || !local_xyz || !local_log_scaling || !local_rotation || !frame_ws)
         return fail(GG_E_BADARG, "NULL argument");
     if (dL_dverts && !frame_grad_ws) return fail(GG_E_BADARG, "frame_grad_ws is required for dL_dverts");
@@ -416,12 +434,24 @@ int gg_mesh_bind_backward(int32_t num_vertices, int32_t num_faces, int32_t num_g
     {
         ScopedKernelTimer kt(K_MESHBWD, s);
         g_launches += launch_mesh_bind_backward(num_faces, num_gaussians, verts, faces, binding, local_xyz, local_log_scaling,
-                                                local_rotation, (const float*)frame_ws, dL_dxyz, dL_dscaling, dL_drotation,
-                                                (float*)frame_grad_ws, dL_dverts, dL_dlocal_xyz, dL_dlocal_log_scaling,
-                                                dL_dlocal_rotation, s);
+                                                local_rotation, barycentric, face_scaling_remembered, (const float*)frame_ws,
+                                                dL_dxyz, dL_dscaling, dL_drotation, (float*)frame_grad_ws, dL_dverts,
+                                                dL_dlocal_xyz, dL_dlocal_log_scaling, dL_dlocal_rotation, s);
     }
     GG_AFTER("mesh_bind_backward");
     return 0;
+}
+
+int gg_mesh_bind_backward(int32_t num_vertices, int32_t num_faces, int32_t num_gaussians, const float* verts,
+                          const int32_t* faces, const int32_t* binding, const float* local_xyz,
+                          const float* local_log_scaling, const float* local_rotation, const void* frame_ws,
+                          void* frame_grad_ws, const float* dL_dxyz, const float* dL_dscaling, const float* dL_drotation,
+                          float* dL_dverts, float* dL_dlocal_xyz, float* dL_dlocal_log_scaling, float* dL_dlocal_rotation,
+                          int device, void* stream) {
+    return gg_mesh_bind_backward_ex(num_vertices, num_faces, num_gaussians, verts, faces, binding, local_xyz,
+                                    local_log_scaling, local_rotation, nullptr, nullptr, frame_ws, frame_grad_ws, dL_dxyz,
+                                    dL_dscaling, dL_drotation, dL_dverts, dL_dlocal_xyz, dL_dlocal_log_scaling,
+                                    dL_dlocal_rotation, device, stream);
 }
 
 // ---- fused photometric loss --------------------------------------------------

@@ -154,12 +154,14 @@ int launch_photometric_bwd(int W, int H, const float* img, const float* gt, cons
                            const float* m2, const float* m3, float c_l1, float c_ss, const float* g_scalar, float* g_img,
                            cudaStream_t s);
 int launch_mesh_bind_forward(int F, int N, const float* verts, const int32_t* faces, const int32_t* binding,
-                             const float* lxyz, const float* lscal, const float* lrot, float* frames, float* o_xyz,
-                             float* o_scal, float* o_rot, cudaStream_t s);
+                             const float* lxyz, const float* lscal, const float* lrot, const float* bary,
+                             const float* scale_rem, float* frames, float* o_xyz, float* o_scal, float* o_rot,
+                             cudaStream_t s);
 int launch_mesh_bind_backward(int F, int N, const float* verts, const int32_t* faces, const int32_t* binding,
-                              const float* lxyz, const float* lscal, const float* lrot, const float* frames,
-                              const float* g_xyz, const float* g_scal, const float* g_rot, float* gF, float* g_verts,
-                              float* gl_xyz, float* gl_scal, float* gl_rot, cudaStream_t s);
+                              const float* lxyz, const float* lscal, const float* lrot, const float* bary,
+                              const float* scale_rem, const float* frames, const float* g_xyz, const float* g_scal,
+                              const float* g_rot, float* gF, float* g_verts, float* gl_xyz, float* gl_scal, float* gl_rot,
+                              cudaStream_t s);
 
 #ifdef __CUDACC__
 // ---------------------------------------------------------------------------------------------

@@ -43,18 +43,28 @@ face_frame_kernel(int F, const float* __restrict__ verts, const int32_t* __restr
     for (int k = 0; k < 4; k++) o[13 + k] = fr.q[k];
 }
 
+// bary != NULL: AvatarGaussianModel anchor (barycentric point of the bound face, scene/avatar_gaussian_model.py:151-154);
+// scale_rem != NULL: get_scaling with the frozen face_scaling_remembered (scene/mesh_gaussian_model.py:98-110).
 __global__ void __launch_bounds__(256)
 bind_fwd_kernel(int N, const float* __restrict__ frames, const int32_t* __restrict__ binding,
                 const float* __restrict__ lxyz, const float* __restrict__ lscal, const float* __restrict__ lrot,
-                float* __restrict__ o_xyz, float* __restrict__ o_scal, float* __restrict__ o_rot) {
+                const float* __restrict__ verts, const int32_t* __restrict__ faces, const float* __restrict__ bary,
+                const float* __restrict__ scale_rem, float* __restrict__ o_xyz, float* __restrict__ o_scal,
+                float* __restrict__ o_rot) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
+    const int f = binding[i];
     FaceFrame fr;
-    load_frame(frames, binding[i], fr);
+    load_frame(frames, f, fr);
     const float4 q = reinterpret_cast<const float4*>(lrot)[i];
     const float lr[4] = {q.x, q.y, q.z, q.w};
+    V3 anchor = fr.center;
+    if (bary) {
+        const V3 bc = ld3(bary, i);
+        anchor = ld3(verts, faces[3 * f]) * bc.x + ld3(verts, faces[3 * f + 1]) * bc.y + ld3(verts, faces[3 * f + 2]) * bc.z;
+    }
     BindOut o;
-    bind_fwd(fr, ld3(lxyz, i), ld3(lscal, i), lr, o);
+    bind_fwd_ex(fr, anchor, scale_rem ? scale_rem[f] : fr.scale, ld3(lxyz, i), ld3(lscal, i), lr, o);
     st3(o_xyz, i, o.xyz);
     st3(o_scal, i, o.scaling);
     reinterpret_cast<float4*>(o_rot)[i] = make_float4(o.rot[0], o.rot[1], o.rot[2], o.rot[3]);
@@ -64,8 +74,9 @@ __global__ void __launch_bounds__(256)
 bind_bwd_kernel(int N, const float* __restrict__ frames, const int32_t* __restrict__ binding,
                 const float* __restrict__ lxyz, const float* __restrict__ lscal, const float* __restrict__ lrot,
                 const float* __restrict__ g_xyz, const float* __restrict__ g_scal, const float* __restrict__ g_rot,
+                const int32_t* __restrict__ faces, const float* __restrict__ bary, const float* __restrict__ scale_rem,
                 float* __restrict__ gl_xyz, float* __restrict__ gl_scal, float* __restrict__ gl_rot,
-                float* __restrict__ gF) {
+                float* __restrict__ gF, float* __restrict__ g_verts) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     const int f = binding[i];
@@ -81,7 +92,18 @@ bind_bwd_kernel(int N, const float* __restrict__ frames, const int32_t* __restri
     }
     V3 a, b;
     float gq[4], g17[17];
-    bind_bwd(fr, ld3(lxyz, i), ld3(lscal, i), lr, gx, gs, gr, a, b, gq, g17);
+    bind_bwd_ex(fr, scale_rem ? scale_rem[f] : fr.scale, scale_rem == nullptr, ld3(lxyz, i), ld3(lscal, i), lr, gx, gs, gr,
+                a, b, gq, g17);
+    if (bary && g_verts) {       // barycentric anchor: its gradient goes straight to the face's three vertices
+        const V3 bc = ld3(bary, i);
+        const float w3[3] = {bc.x, bc.y, bc.z};
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            float* dst = g_verts + 3 * (size_t)faces[3 * f + k];
+            atomicAdd(dst, w3[k] * gx.x); atomicAdd(dst + 1, w3[k] * gx.y); atomicAdd(dst + 2, w3[k] * gx.z);
+        }
+        g17[10] = g17[11] = g17[12] = 0.f;
+    }
     if (gl_xyz) st3(gl_xyz, i, a);
     if (gl_scal) st3(gl_scal, i, b);
     if (gl_rot) reinterpret_cast<float4*>(gl_rot)[i] = make_float4(gq[0], gq[1], gq[2], gq[3]);
@@ -112,22 +134,29 @@ face_frame_bwd_kernel(int F, const float* __restrict__ verts, const int32_t* __r
 }
 
 int launch_mesh_bind_forward(int F, int N, const float* verts, const int32_t* faces, const int32_t* binding,
-                             const float* lxyz, const float* lscal, const float* lrot, float* frames, float* o_xyz,
-                             float* o_scal, float* o_rot, cudaStream_t s) {
+                             const float* lxyz, const float* lscal, const float* lrot, const float* bary,
+                             const float* scale_rem, float* frames, float* o_xyz, float* o_scal, float* o_rot,
+                             cudaStream_t s) {
     int n = 0;
     if (F > 0) { face_frame_kernel<<<(F + 255) / 256, 256, 0, s>>>(F, verts, faces, frames); n++; }
-    if (N > 0) { bind_fwd_kernel<<<(N + 255) / 256, 256, 0, s>>>(N, frames, binding, lxyz, lscal, lrot, o_xyz, o_scal, o_rot); n++; }
+    if (N > 0) {
+        bind_fwd_kernel<<<(N + 255) / 256, 256, 0, s>>>(N, frames, binding, lxyz, lscal, lrot, verts, faces, bary, scale_rem,
+                                                        o_xyz, o_scal, o_rot);
+        n++;
+    }
     return n;
 }
 
 int launch_mesh_bind_backward(int F, int N, const float* verts, const int32_t* faces, const int32_t* binding,
-                              const float* lxyz, const float* lscal, const float* lrot, const float* frames,
-                              const float* g_xyz, const float* g_scal, const float* g_rot, float* gF, float* g_verts,
-                              float* gl_xyz, float* gl_scal, float* gl_rot, cudaStream_t s) {
+                              const float* lxyz, const float* lscal, const float* lrot, const float* bary,
+                              const float* scale_rem, const float* frames, const float* g_xyz, const float* g_scal,
+                              const float* g_rot, float* gF, float* g_verts, float* gl_xyz, float* gl_scal, float* gl_rot,
+                              cudaStream_t s) {
     int n = 0;
     if (N > 0) {
-        bind_bwd_kernel<<<(N + 255) / 256, 256, 0, s>>>(N, frames, binding, lxyz, lscal, lrot, g_xyz, g_scal, g_rot,
-                                                        gl_xyz, gl_scal, gl_rot, g_verts ? gF : nullptr);
+        bind_bwd_kernel<<<(N + 255) / 256, 256, 0, s>>>(N, frames, binding, lxyz, lscal, lrot, g_xyz, g_scal, g_rot, faces,
+                                                        bary, scale_rem, gl_xyz, gl_scal, gl_rot,
+                                                        g_verts ? gF : nullptr, g_verts);
         n++;
     }
     if (F > 0 && g_verts) { face_frame_bwd_kernel<<<(F + 255) / 256, 256, 0, s>>>(F, verts, faces, gF, g_verts); n++; }

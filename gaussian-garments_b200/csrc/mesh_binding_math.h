@@ -191,21 +191,31 @@ GG_HD void qnormalize_bwd(const float* y, float n, const float* gy, float* gx) {
 
 struct BindOut { V3 xyz; V3 scaling; float rot[4]; };
 
-GG_HD void bind_fwd(const FaceFrame& f, V3 lxyz, V3 lscal, const float* lrot, BindOut& o) {
+// `anchor`: where the local frame sits -- the face centre (MeshGaussianModel.get_xyz, scene/mesh_gaussian_model.py:124-128)
+// or the barycentric point a v0 + b v1 + c v2 (AvatarGaussianModel.get_xyz / get_final_xyz / get_barycentric_3d,
+// scene/avatar_gaussian_model.py:140-159).  `scal_scale`: the face scale get_scaling multiplies with -- the current one,
+// or the frozen `face_scaling_remembered` (scene/mesh_gaussian_model.py:98-110), which carries no gradient.
+GG_HD void bind_fwd_ex(const FaceFrame& f, V3 anchor, float scal_scale, V3 lxyz, V3 lscal, const float* lrot, BindOut& o) {
     const V3 r = v3(f.R[0] * lxyz.x + f.R[1] * lxyz.y + f.R[2] * lxyz.z, f.R[3] * lxyz.x + f.R[4] * lxyz.y + f.R[5] * lxyz.z,
                     f.R[6] * lxyz.x + f.R[7] * lxyz.y + f.R[8] * lxyz.z);
-    o.xyz = r * f.scale + f.center;
-    o.scaling = v3(expf(lscal.x) * f.scale, expf(lscal.y) * f.scale, expf(lscal.z) * f.scale);
+    o.xyz = r * f.scale + anchor;
+    o.scaling = v3(expf(lscal.x) * scal_scale, expf(lscal.y) * scal_scale, expf(lscal.z) * scal_scale);
     float rl[4], fq[4], w[4];
     qnormalize(lrot, rl);
     qnormalize(f.q, fq);
     qmul(fq, rl, w);
     qnormalize(w, o.rot);
 }
+GG_HD void bind_fwd(const FaceFrame& f, V3 lxyz, V3 lscal, const float* lrot, BindOut& o) {
+    bind_fwd_ex(f, f.center, f.scale, lxyz, lscal, lrot, o);
+}
 
-// gradients wrt outputs -> gradients wrt local params and wrt the face frame (17 floats, to be accumulated)
-GG_HD void bind_bwd(const FaceFrame& f, V3 lxyz, V3 lscal, const float* lrot, V3 g_xyz, V3 g_scal, const float* g_rot,
-                    V3& gl_xyz, V3& gl_scal, float* gl_rot, float* gF /*[17]: R9, scale, center3, q4*/) {
+// gradients wrt outputs -> gradients wrt local params and wrt the face frame (17 floats, to be accumulated).
+// gF[10..12] is the gradient of the ANCHOR (= centre slots for the face-centre variant; the barycentric variant
+// scatters it to the three vertices itself).  scale_is_live = false: get_scaling used a frozen face scale.
+GG_HD void bind_bwd_ex(const FaceFrame& f, float scal_scale, bool scale_is_live, V3 lxyz, V3 lscal, const float* lrot,
+                       V3 g_xyz, V3 g_scal, const float* g_rot, V3& gl_xyz, V3& gl_scal, float* gl_rot,
+                       float* gF /*[17]: R9, scale, anchor3, q4*/) {
     const V3 r = v3(f.R[0] * lxyz.x + f.R[1] * lxyz.y + f.R[2] * lxyz.z, f.R[3] * lxyz.x + f.R[4] * lxyz.y + f.R[5] * lxyz.z,
                     f.R[6] * lxyz.x + f.R[7] * lxyz.y + f.R[8] * lxyz.z);
     const V3 gs = g_xyz * f.scale;                          // gradient wrt r
@@ -215,9 +225,9 @@ GG_HD void bind_bwd(const FaceFrame& f, V3 lxyz, V3 lscal, const float* lrot, V3
     gF[3] = gs.y * lxyz.x; gF[4] = gs.y * lxyz.y; gF[5] = gs.y * lxyz.z;
     gF[6] = gs.z * lxyz.x; gF[7] = gs.z * lxyz.y; gF[8] = gs.z * lxyz.z;
     const V3 ex = v3(expf(lscal.x), expf(lscal.y), expf(lscal.z));
-    gF[9] = dot(g_xyz, r) + g_scal.x * ex.x + g_scal.y * ex.y + g_scal.z * ex.z;
+    gF[9] = dot(g_xyz, r) + (scale_is_live ? g_scal.x * ex.x + g_scal.y * ex.y + g_scal.z * ex.z : 0.f);
     gF[10] = g_xyz.x; gF[11] = g_xyz.y; gF[12] = g_xyz.z;
-    gl_scal = v3(g_scal.x * ex.x * f.scale, g_scal.y * ex.y * f.scale, g_scal.z * ex.z * f.scale);
+    gl_scal = v3(g_scal.x * ex.x * scal_scale, g_scal.y * ex.y * scal_scale, g_scal.z * ex.z * scal_scale);
     float rl[4], fq[4], w[4], out[4];
     const float n_rl = qnormalize(lrot, rl);
     const float n_fq = qnormalize(f.q, fq);
@@ -228,6 +238,10 @@ GG_HD void bind_bwd(const FaceFrame& f, V3 lxyz, V3 lscal, const float* lrot, V3
     qmul_bwd(fq, rl, gw, gfq, grl);
     qnormalize_bwd(rl, n_rl, grl, gl_rot);
     qnormalize_bwd(fq, n_fq, gfq, gF + 13);
+}
+GG_HD void bind_bwd(const FaceFrame& f, V3 lxyz, V3 lscal, const float* lrot, V3 g_xyz, V3 g_scal, const float* g_rot,
+                    V3& gl_xyz, V3& gl_scal, float* gl_rot, float* gF) {
+    bind_bwd_ex(f, f.scale, true, lxyz, lscal, lrot, g_xyz, g_scal, g_rot, gl_xyz, gl_scal, gl_rot, gF);
 }
 
 }  // namespace ggmb

@@ -150,6 +150,27 @@ int gg_mesh_bind_backward(int32_t num_vertices, int32_t num_faces, int32_t num_g
                           const float* dL_drotation, float* dL_dverts, float* dL_dlocal_xyz,
                           float* dL_dlocal_log_scaling, float* dL_dlocal_rotation, int device, void* stream);
 
+/* `_ex` variants: the two remaining forms of the reference's binding.
+ *   barycentric[N,3] != NULL  -> AvatarGaussianModel: the local frame is anchored at a*v0 + b*v1 + c*v2 of the bound
+ *                                face instead of its centre (get_xyz / get_final_xyz / get_barycentric_3d,
+ *                                /root/reference/scene/avatar_gaussian_model.py:140-159; pass `local_xyz` = _xyz or the
+ *                                per-frame `local_xyz` of scene/avatar_net.py:82); its gradient goes to the 3 vertices.
+ *   face_scaling_remembered[F] != NULL -> get_scaling multiplies with this frozen per-face scale (remember_scaling,
+ *                                /root/reference/scene/mesh_gaussian_model.py:98-110) and sends no gradient to the mesh.
+ * With both NULL they are the functions above.                                                                      */
+int gg_mesh_bind_forward_ex(int32_t num_vertices, int32_t num_faces, int32_t num_gaussians, const float* verts,
+                            const int32_t* faces, const int32_t* binding, const float* local_xyz,
+                            const float* local_log_scaling, const float* local_rotation, const float* barycentric,
+                            const float* face_scaling_remembered, void* frame_ws, float* out_xyz, float* out_scaling,
+                            float* out_rotation, int device, void* stream);
+int gg_mesh_bind_backward_ex(int32_t num_vertices, int32_t num_faces, int32_t num_gaussians, const float* verts,
+                             const int32_t* faces, const int32_t* binding, const float* local_xyz,
+                             const float* local_log_scaling, const float* local_rotation, const float* barycentric,
+                             const float* face_scaling_remembered, const void* frame_ws, void* frame_grad_ws,
+                             const float* dL_dxyz, const float* dL_dscaling, const float* dL_drotation, float* dL_dverts,
+                             float* dL_dlocal_xyz, float* dL_dlocal_log_scaling, float* dL_dlocal_rotation, int device,
+                             void* stream);
+
 /* ---- fused photometric loss ("next" row N2) -------------------------------------------------
  * Replaces l1_loss(image, gt, mask) and ssim(image, gt, mask) of /root/reference/utils/loss_utils.py:17-69
  * as used at s2_registration.py:259-260 / s3_appearance.py:132-133.  image, gt: [3,H,W]; mask: [1,H,W]

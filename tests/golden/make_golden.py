@@ -10,6 +10,8 @@ restate:
                scene/gaussian_model.py:27-31
   camera.npz   utils/graphics_utils.py:getWorld2View2 / getProjectionMatrix / focal2fov composed
                exactly as scene/cameras.py:53-62, plus projected pixel centres of sample points
+  mesh.npz     utils/graphics_utils.py:118-137 compute_face_orientation(return_scale=True) on a random triangle
+               soup (incl. one degenerate face) + the face centres of scene/mesh_gaussian_model.py:92
 Shims used only here: `open3d` is stubbed (utils/general_utils.py:18 imports it but the two
 functions we call do not use it) and torch.zeros(..., device="cuda") is redirected to CPU
 (utils/general_utils.py:75,93,112 hard-code the device).
@@ -123,7 +125,20 @@ def main():
         if mask is not None:
             out[f"{tag}_mask"] = mask.numpy()
     np.savez(os.path.join(OUT, "loss.npz"), **out)
-    print("wrote sh.npz cov3d.npz camera.npz loss.npz to", OUT)
+
+    # ---- mesh face frames (utils/graphics_utils.py:118-137 compute_face_orientation, return_scale=True) --------
+    gm = torch.Generator().manual_seed(4242)
+    V, F = 40, 64
+    verts = torch.randn(V, 3, generator=gm) * 0.3
+    faces = torch.stack([torch.randperm(V, generator=gm)[:3] for _ in range(F)]).long()
+    faces[-1] = torch.tensor([0, 1, 1])                       # degenerate face: exercises the 1e-20 clamps
+    orient, scale = gu.compute_face_orientation(verts, faces, return_scale=True)
+    vd = verts.double()
+    orient64, scale64 = gu.compute_face_orientation(vd, faces, return_scale=True)
+    np.savez(os.path.join(OUT, "mesh.npz"), verts=verts.numpy(), faces=faces.numpy(), orientation=orient.numpy(),
+             scale=scale.numpy(), orientation64=orient64.numpy(), scale64=scale64.numpy(),
+             center=verts[faces].mean(1).numpy())
+    print("wrote sh.npz cov3d.npz camera.npz loss.npz mesh.npz to", OUT)
 
 
 if __name__ == "__main__":

@@ -462,38 +462,72 @@ def test_lazy_path_equals_tma_path_when_tiles_saturate(monkeypatch):
 
 
 # ------------------------------------------------------------------------------------ N1: fused mesh binding
-def test_fused_mesh_binding_matches_torch_chain():
-    """gg_mesh_bind_forward/backward vs autograd through the restated reference chain
-    (scene/mesh_gaussian_model.py:90-128), incl. gradients to mesh.v."""
+@pytest.mark.parametrize("avatar,remembered", [(False, False), (True, False), (False, True), (True, True)])
+def test_fused_mesh_binding_matches_torch_chain(avatar, remembered):
+    """gg_mesh_bind_forward_ex/backward_ex vs autograd (fp64) through oracle/mesh_chain.py -- the golden-pinned
+    restatement of scene/mesh_gaussian_model.py:90-128 and, with `avatar`, of the barycentric anchor of
+    scene/avatar_gaussian_model.py:140-159 (get_xyz AND get_final_xyz); `remembered` = face_scaling_remembered branch
+    (scene/mesh_gaussian_model.py:98-110).  Includes the gradient to mesh.v."""
+    from oracle import mesh_chain as mc
     dev = torch.device("cuda:0")
     g = torch.Generator().manual_seed(11)
     m = gg.scenes.MeshBoundGaussians(n_faces_around=40, n_along=12, per_face=6, seed=5)
     m.mesh_v = m.mesh_v + 0.005 * torch.randn(m.mesh_v.shape, generator=g)
     m._rotation = torch.randn(m._rotation.shape, generator=g)
-    m.to(dev)
-    N = m.binding.shape[0]
-    G = [torch.randn(N, 3, generator=g).to(dev), torch.randn(N, 3, generator=g).to(dev), torch.randn(N, 4, generator=g).to(dev)]
+    N, F = m.binding.shape[0], m.mesh_f.shape[0]
+    bc = None
+    if avatar:
+        bc = torch.rand(N, 3, generator=g) + 0.05
+        bc = bc / bc.sum(1, keepdim=True)
+    rem = (0.8 + 0.4 * torch.rand(F, 1, generator=g)) * 0.01 if remembered else None
+    local_final = m._xyz + 0.02 * torch.randn(N, 3, generator=g)          # AvatarNet: local_xyz = _xyz + offset
+    G = [torch.randn(N, 3, generator=g), torch.randn(N, 3, generator=g), torch.randn(N, 4, generator=g)]
 
-    def leaves():
-        return [getattr(m, k).detach().clone().requires_grad_(True) for k in ("mesh_v", "_xyz", "_scaling", "_rotation")]
+    for final in ((False, True) if avatar else (False,)):
+        lx_src = local_final if final else m._xyz
+        a = [t.detach().clone().to(dev).requires_grad_(True) for t in (m.mesh_v, lx_src, m._scaling, m._rotation)]
+        xyz, sc, ro = gg.bind_to_mesh(a[0], m.mesh_f.to(dev), m.binding.to(dev), a[1], a[2], a[3],
+                                      barycentric=None if bc is None else [bc[:, k].to(dev) for k in range(3)],
+                                      face_scaling_remembered=None if rem is None else rem.to(dev))
+        ((xyz * G[0].to(dev)).sum() + (sc * G[1].to(dev)).sum() + (ro * G[2].to(dev)).sum()).backward()
 
-    a = leaves()
-    xyz, sc, ro = gg.bind_to_mesh(a[0], m.mesh_f, m.binding, a[1], a[2], a[3])
-    ((xyz * G[0]).sum() + (sc * G[1]).sum() + (ro * G[2]).sum()).backward()
+        b = [t.detach().double().requires_grad_(True) for t in (m.mesh_v, lx_src, m._scaling, m._rotation)]
+        ref = mc.MeshChain(b[0], m.mesh_f, m.binding, b[1], b[2], b[3], gs_bc=None if bc is None else bc.double(),
+                           local_xyz=b[1])
+        ref.update_face_coor()
+        if rem is not None:
+            ref.face_scaling_remembered = rem.double()
+        r_xyz = ref.get_final_xyz if final else ref.get_xyz
+        ((r_xyz * G[0].double()).sum() + (ref.get_scaling * G[1].double()).sum() + (ref.get_rotation * G[2].double()).sum()).backward()
 
-    b = [t.double() for t in leaves()]
-    b = [t.detach().requires_grad_(True) for t in b]
-    ref = gg.scenes.MeshBoundGaussians.__new__(gg.scenes.MeshBoundGaussians)
-    ref.mesh_f, ref.binding = m.mesh_f, m.binding
-    ref.mesh_v, ref._xyz, ref._scaling, ref._rotation = b
-    ref.update_face_coor()
-    ((ref.get_xyz * G[0].double()).sum() + (ref.get_scaling * G[1].double()).sum() + (ref.get_rotation * G[2].double()).sum()).backward()
+        assert torch.allclose(xyz.cpu(), r_xyz.float(), atol=2e-6)
+        assert torch.allclose(sc.cpu(), ref.get_scaling.float(), atol=1e-7, rtol=1e-5)
+        assert torch.allclose(ro.cpu(), ref.get_rotation.float(), atol=2e-6)
+        for name, x, y in zip(("mesh_v", "_xyz", "_scaling", "_rotation"), a, b):
+            assert h.rel_inf(x.grad.cpu(), y.grad.float()) < 1e-3, (name, final)
 
-    assert torch.allclose(xyz, ref.get_xyz.float(), atol=2e-6)
-    assert torch.allclose(sc, ref.get_scaling.float(), atol=1e-7, rtol=1e-5)
-    assert torch.allclose(ro, ref.get_rotation.float(), atol=2e-6)
-    for name, x, y in zip(("mesh_v", "_xyz", "_scaling", "_rotation"), a, b):
-        assert h.rel_inf(x.grad, y.grad.float()) < 1e-3, name
+
+def test_fused_mesh_binding_provider_tracks_rebinding_and_rejects_bad_indices():
+    """the int32 copies of mesh.f / binding must follow a re-assigned or in-place edited `binding` of the
+    SAME length (prune + clone, scene/mesh_gaussian_model.py:130-208); out-of-range indices raise like torch indexing."""
+    dev = torch.device("cuda:0")
+    m = gg.scenes.MeshBoundGaussians(n_faces_around=24, n_along=6, per_face=2, seed=3).to(dev)
+    prov = gg.FusedMeshBinding(m)
+    x0, _, _ = prov.world()
+    m.update_face_coor()
+    assert torch.allclose(x0, m.get_xyz, atol=2e-6)
+    m.binding = m.binding.flip(0).contiguous()                 # new tensor, same length
+    x1, _, _ = prov.world()
+    assert torch.allclose(x1, m.get_xyz, atol=2e-6) and not torch.allclose(x1, x0, atol=1e-4)
+    m.binding[:10] = 0                                          # in-place edit (version bump)
+    x2, _, _ = prov.world()
+    assert torch.allclose(x2, m.get_xyz, atol=2e-6)
+    bad = m.binding.clone()
+    bad[3] = m.mesh_f.shape[0]                                  # one past the last face
+    with pytest.raises(IndexError):
+        gg.bind_to_mesh(m.mesh_v, m.mesh_f, bad, m._xyz, m._scaling, m._rotation)
+    with pytest.raises(IndexError):
+        gg.bind_to_mesh(m.mesh_v, m.mesh_f, m.binding[:-1], m._xyz, m._scaling, m._rotation)
 
 
 def test_fused_mesh_binding_feeds_the_rasterizer():
