@@ -22,5 +22,6 @@ from .rasterizer import (  # noqa: F401
 from . import cameras, scenes  # noqa: F401
 from .mesh_binding import bind_to_mesh, FusedMeshBinding  # noqa: F401
 from .losses import photometric_loss  # noqa: F401
+from .visibility import cast_rays_from_point, visible_mask, visible_mask_multi  # noqa: F401
 
 __version__ = "0.1.0"

@@ -14,7 +14,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.environ.get("GG_RASTER_LIB") or os.path.join(CSRC, "libgg_raster.so")   # override: dev experiments
-SOURCES = ["project.cu", "binning.cu", "blend_fwd.cu", "blend_bwd.cu", "blend_bwd2.cu", "preprocess_bwd.cu", "mesh_binding.cu", "photometric.cu", "c_api.cu"]
+SOURCES = ["project.cu", "binning.cu", "blend_fwd.cu", "blend_bwd.cu", "blend_bwd2.cu", "preprocess_bwd.cu", "mesh_binding.cu", "photometric.cu", "visibility.cu", "c_api.cu"]
 HEADERS = ["common.cuh", "mesh_binding_math.h", os.path.join("..", "..", "include", "gg_raster.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -50,7 +50,7 @@ def _needs_build() -> bool:
 # project.cu is compiled with -fmad=false: without FMA contraction its IEEE +,-,*,/,sqrt arithmetic is
 # bit-identical to the CPU oracle's (gcc -ffp-contract=off), so every DISCRETE decision taken from the
 # projected geometry (cull, radius, tile rectangle, depth order) agrees with the oracle by construction.
-PER_FILE_FLAGS = {"project.cu": ["-fmad=false"]}
+PER_FILE_FLAGS = {"project.cu": ["-fmad=false"], "visibility.cu": ["-fmad=false"]}   # ray casts: bit-identical to oracle/raycast_oracle.c
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -120,6 +120,8 @@ def load():
         lib.gg_mesh_bind_backward.argtypes = [C.c_int32] * 3 + [vp] * 15 + [i32, vp]
         lib.gg_mesh_bind_forward_ex.argtypes = [C.c_int32] * 3 + [vp] * 12 + [i32, vp]
         lib.gg_mesh_bind_backward_ex.argtypes = [C.c_int32] * 3 + [vp] * 17 + [i32, vp]
+        lib.gg_cast_rays_workspace_bytes.argtypes = [C.c_int32, C.c_int32, P(sz), P(C.c_int64)]
+        lib.gg_cast_rays_from_point.argtypes = [C.c_int32] * 3 + [vp] * 6 + [i64, C.c_int32, vp, vp, i32, vp]
         lib.gg_photometric_workspace_bytes.argtypes = [C.c_int32, C.c_int32, P(sz)]
         lib.gg_photometric_forward.argtypes = [C.c_int32, C.c_int32, vp, vp, vp, vp, C.c_int32, i32, vp]
         lib.gg_photometric_backward.argtypes = [C.c_int32, C.c_int32, vp, vp, vp, vp, C.c_float, C.c_float, vp, vp, i32, vp]
@@ -132,7 +134,8 @@ def load():
                      "gg_forward_project", "gg_forward_color", "gg_forward_render", "gg_backward",
                      "gg_mark_visible", "gg_debug_read_geom", "gg_debug_read_binning", "gg_kernel_timing", "gg_kernel_times",
                      "gg_mesh_bind_workspace_bytes", "gg_mesh_bind_forward", "gg_mesh_bind_backward",
-                     "gg_mesh_bind_forward_ex", "gg_mesh_bind_backward_ex",
+                     "gg_mesh_bind_forward_ex", "gg_mesh_bind_backward_ex", "gg_cast_rays_workspace_bytes",
+                     "gg_cast_rays_from_point",
                      "gg_photometric_workspace_bytes", "gg_photometric_forward", "gg_photometric_backward"):
             getattr(lib, name).restype = C.c_int
         if lib.gg_abi_version() != 1:
@@ -153,7 +156,8 @@ EXPORTED_SYMBOLS = [
     "gg_forward_render", "gg_backward", "gg_mark_visible", "gg_debug_read_geom", "gg_debug_read_binning",
     "gg_kernel_timing",
     "gg_kernel_count", "gg_kernel_name", "gg_kernel_times", "gg_mesh_bind_workspace_bytes", "gg_mesh_bind_forward",
-    "gg_mesh_bind_backward", "gg_mesh_bind_forward_ex", "gg_mesh_bind_backward_ex", "gg_photometric_workspace_bytes", "gg_photometric_forward", "gg_photometric_backward",
+    "gg_mesh_bind_backward", "gg_mesh_bind_forward_ex", "gg_mesh_bind_backward_ex", "gg_cast_rays_workspace_bytes",
+    "gg_cast_rays_from_point", "gg_photometric_workspace_bytes", "gg_photometric_forward", "gg_photometric_backward",
 ]
 
 

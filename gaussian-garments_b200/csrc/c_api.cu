@@ -14,10 +14,10 @@ thread_local char g_err[512] = "";
 // worker thread: launch counts and per-kernel events must be visible from the caller's thread.
 std::atomic<int64_t> g_launches{0};
 
-enum KernelSlot { K_PROJECT = 0, K_SCAN, K_SHCOLOR, K_EMIT, K_SORTPACK, K_BLENDFWD, K_BLENDBWD, K_PREBWD, K_MESHFWD, K_MESHBWD, K_LOSSFWD, K_LOSSBWD, K_COUNT };
+enum KernelSlot { K_PROJECT = 0, K_SCAN, K_SHCOLOR, K_EMIT, K_SORTPACK, K_BLENDFWD, K_BLENDBWD, K_PREBWD, K_MESHFWD, K_MESHBWD, K_LOSSFWD, K_LOSSBWD, K_RAYCAST, K_COUNT };
 const char* const kKernelNames[K_COUNT] = {"project", "tile_scan", "sh_color", "emit", "sort_pack",
                                            "blend_fwd", "blend_bwd", "preprocess_bwd", "mesh_bind_fwd",
-                                           "mesh_bind_bwd", "photometric_fwd", "photometric_bwd"};
+                                           "mesh_bind_bwd", "photometric_fwd", "photometric_bwd", "cast_rays"};
 std::atomic<int> g_timing{0};
 std::mutex g_timing_mu;
 cudaEvent_t g_ev[K_COUNT][2];
@@ -452,6 +452,36 @@ int gg_mesh_bind_backward(int32_t num_vertices, int32_t num_faces, int32_t num_g
                                     local_log_scaling, local_rotation, nullptr, nullptr, frame_ws, frame_grad_ws, dL_dxyz,
                                     dL_dscaling, dL_drotation, dL_dverts, dL_dlocal_xyz, dL_dlocal_log_scaling,
                                     dL_dlocal_rotation, device, stream);
+}
+
+// ---- on-device visibility ray cast -------------------------------------------
+int gg_cast_rays_workspace_bytes(int32_t num_vertices, int32_t num_faces, size_t* ws_bytes, int64_t* list_capacity) {
+    if (num_vertices < 0 || num_faces < 0) return fail(GG_E_BADARG, "negative size");
+    const int64_t cap = 32ll * num_faces + 65536;      // cell-list entries; more than this -> brute-force kernel
+    if (list_capacity) *list_capacity = cap;
+    if (ws_bytes) *ws_bytes = vis_workspace_bytes(num_vertices, cap);
+    return 0;
+}
+
+int gg_cast_rays_from_point(int32_t num_vertices, int32_t num_faces, int32_t num_rays, const float* verts,
+                            const int32_t* faces, const float* targets, const float* origin, const float* look_at,
+                            void* ws, int64_t list_capacity, int32_t force_bruteforce, int32_t* primitive_ids,
+                            float* t_hit, int device, void* stream) {
+    if (num_vertices < 0 || num_faces < 0 || num_rays < 0) return fail(GG_E_BADARG, "negative size");
+    if (num_rays == 0) return 0;
+    if (!targets || !origin || !look_at || !ws || !primitive_ids) return fail(GG_E_BADARG, "NULL argument");
+    if (num_faces > 0 && (!verts || !faces)) return fail(GG_E_BADARG, "NULL mesh");
+    if (list_capacity < 0 || list_capacity > 0xfffffff0ll) return fail(GG_E_BADARG, "list_capacity out of range");
+    GG_CUDA(cudaSetDevice(device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const gg_view* view = nullptr;
+    {
+        ScopedKernelTimer kt(K_RAYCAST, s);
+        g_launches += launch_cast_rays(num_vertices, num_faces, num_rays, verts, faces, targets, origin, look_at, ws,
+                                       list_capacity, force_bruteforce, primitive_ids, t_hit, s);
+    }
+    GG_AFTER("cast_rays");
+    return 0;
 }
 
 // ---- fused photometric loss --------------------------------------------------

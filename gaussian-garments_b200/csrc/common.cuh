@@ -163,6 +163,11 @@ int launch_mesh_bind_backward(int F, int N, const float* verts, const int32_t* f
                               const float* g_rot, float* gF, float* g_verts, float* gl_xyz, float* gl_scal, float* gl_rot,
                               cudaStream_t s);
 
+size_t vis_workspace_bytes(int64_t V, int64_t capacity);
+int launch_cast_rays(int V, int F, int N, const float* verts, const int32_t* faces, const float* targets,
+                     const float* origin, const float* look_at, void* ws_base, int64_t capacity, int force_bruteforce,
+                     int32_t* prim, float* t_hit, cudaStream_t s);
+
 #ifdef __CUDACC__
 // ---------------------------------------------------------------------------------------------
 // device helpers

@@ -171,6 +171,22 @@ int gg_mesh_bind_backward_ex(int32_t num_vertices, int32_t num_faces, int32_t nu
                              float* dL_dlocal_xyz, float* dL_dlocal_log_scaling, float* dL_dlocal_rotation, int device,
                              void* stream);
 
+/* ---- on-device visibility ray cast ("next" row N3) ----------------------------------------------
+ * Replaces the GPU -> CPU -> Embree -> GPU round trip of get_visible_mask
+ * (/root/reference/scene/avatar_gaussian_model.py:227-263, /root/reference/inference.py:285-316): one ray per target
+ * from `origin` (the camera centre, device float[3]) along (target - origin)/|target - origin| against the triangle
+ * mesh verts[V,3] / faces[F,3] (int32).  primitive_ids[N] (int32) receives what open3d's
+ * RaycastingScene.cast_rays()['primitive_ids'] holds -- the index of the closest triangle hit -- with -1 instead of
+ * INVALID_ID; t_hit[N] (may be NULL) the hit distance (inf when nothing is hit).  `look_at` (device float[3], e.g. the
+ * mesh centroid) only orients the projection grid that accelerates the cast; the answer does not depend on it.
+ * The caller forms the masks: primitive_ids == binding (avatar model), geometry_of(primitive_ids) == garment | no hit
+ * (inference).  ws / list_capacity from gg_cast_rays_workspace_bytes; force_bruteforce != 0 skips the grid.       */
+int gg_cast_rays_workspace_bytes(int32_t num_vertices, int32_t num_faces, size_t* ws_bytes, int64_t* list_capacity);
+int gg_cast_rays_from_point(int32_t num_vertices, int32_t num_faces, int32_t num_rays, const float* verts,
+                            const int32_t* faces, const float* targets, const float* origin, const float* look_at,
+                            void* ws, int64_t list_capacity, int32_t force_bruteforce, int32_t* primitive_ids,
+                            float* t_hit, int device, void* stream);
+
 /* ---- fused photometric loss ("next" row N2) -------------------------------------------------
  * Replaces l1_loss(image, gt, mask) and ssim(image, gt, mask) of /root/reference/utils/loss_utils.py:17-69
  * as used at s2_registration.py:259-260 / s3_appearance.py:132-133.  image, gt: [3,H,W]; mask: [1,H,W]

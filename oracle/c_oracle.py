@@ -28,7 +28,8 @@ class _Params(C.Structure):
 def build(force: bool = False) -> str:
     so = os.path.join(_HERE, "libgg_oracle.so")
     src = os.path.join(_HERE, "gg_oracle.c")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+    srcs = [src, os.path.join(_HERE, "raycast_oracle.c"), os.path.join(_HERE, "Makefile")]
+    if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(p) for p in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-B", "libgg_oracle.so"], stdout=subprocess.DEVNULL)
     return so
 
@@ -55,6 +56,8 @@ def lib():
         _LIB.ggo_get_binning.argtypes = [vp] * 5
         _LIB.ggo_get_binning.restype = C.c_int
         _LIB.ggo_set_num_threads.argtypes = [C.c_int]
+        _LIB.ggo_cast_rays_from_point.argtypes = [C.c_int32] * 3 + [vp] * 6
+        _LIB.ggo_cast_rays_from_point.restype = C.c_int
     return _LIB
 
 
@@ -170,3 +173,19 @@ def num_threads() -> int:
 
 def set_num_threads(n: int):
     lib().ggo_set_num_threads(int(n))
+
+
+def cast_rays_from_point(verts, faces, targets, origin):
+    """Row N3's oracle (oracle/raycast_oracle.c): first triangle hit by each ray origin -> target.
+    -> (primitive_ids int32 [N] with -1 = no hit, t_hit float32 [N])"""
+    v = verts.detach().to("cpu", torch.float32).contiguous()
+    f = faces.detach().to("cpu", torch.int32).contiguous()
+    t = targets.detach().to("cpu", torch.float32).contiguous()
+    o = origin.detach().to("cpu", torch.float32).contiguous()
+    N = t.shape[0]
+    prim = torch.zeros(max(N, 1), dtype=torch.int32)
+    th = torch.zeros(max(N, 1))
+    rc = lib().ggo_cast_rays_from_point(v.shape[0], f.shape[0], N, _p(v), _p(f), _p(t), _p(o), _p(prim), _p(th))
+    if rc != 0:
+        raise RuntimeError("ggo_cast_rays_from_point failed")
+    return prim[:N], th[:N]

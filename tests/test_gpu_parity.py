@@ -919,3 +919,67 @@ def test_reference_facade_trace_replay():
             colors_precomp=None, opacities=kw["opacities"].detach(), scales=kw["scales"].detach(),
             rotations=kw["rotations"].detach(), cov3D_precomp=None)
     assert float((images["render_compute_cov3D_python"] - ref_img).abs().max()) < 1e-4
+
+
+# ------------------------------------------------------------------------------------ N3: on-device visibility mask
+def _garment_scene(seed=2, n_around=120, n_along=40, per_face=4):
+    g = torch.Generator().manual_seed(seed)
+    verts, faces = gg.scenes.cylinder_mesh(n_around=n_around, n_along=n_along)
+    F = faces.shape[0]
+    binding = torch.arange(F).repeat_interleave(per_face)
+    bc = torch.rand(binding.shape[0], 3, generator=g) + 0.02
+    bc = bc / bc.sum(1, keepdim=True)
+    tri = verts[faces][binding]
+    pts = bc[:, 0:1] * tri[:, 0] + bc[:, 1:2] * tri[:, 1] + bc[:, 2:3] * tri[:, 2]      # get_barycentric_3d
+    return verts, faces, binding, pts
+
+
+@pytest.mark.parametrize("cam", [(0.0, 0.6, 3.0), (2.1, 1.4, -1.7), (0.05, 0.6, 0.02)])
+def test_visibility_mask_is_bit_equal_to_the_cpu_raycast_oracle(cam):
+    """Row N3: gg_cast_rays_from_point (projection-grid path AND forced brute force) vs oracle/raycast_oracle.c on
+    the synthetic garment cylinder -- primitive ids identical for every ray, hence bit-equal boolean masks for the
+    avatar semantics (scene/avatar_gaussian_model.py:227-263).  The third camera sits INSIDE the cylinder: vertices
+    fall behind the pinhole plane and the kernel must route itself to the brute-force path."""
+    dev = torch.device("cuda:0")
+    verts, faces, binding, pts = _garment_scene()
+    origin = torch.tensor(cam)
+    ref_prim, ref_t = h.c_oracle.cast_rays_from_point(verts, faces, pts, origin)
+    for force in (False, True):
+        prim, t = gg.cast_rays_from_point(verts.to(dev), faces.to(dev), pts.to(dev), origin.to(dev),
+                                          force_bruteforce=force, return_t=True)
+        assert torch.equal(prim.cpu(), ref_prim), f"{int((prim.cpu() != ref_prim).sum())} rays differ (force={force})"
+        assert torch.equal(t.cpu(), ref_t)
+    vis = gg.visible_mask(origin.to(dev), verts.to(dev), faces.to(dev), pts.to(dev), binding.to(dev))
+    ref_vis = ref_prim == binding.to(torch.int32)
+    assert vis.dtype == torch.bool and torch.equal(vis.cpu(), ref_vis)
+    frac = float(ref_vis.float().mean())
+    assert 0.2 < frac < 0.99 if abs(cam[0]) + abs(cam[2]) > 1 else frac > 0.9     # outside: the far half is occluded
+    h._note("visibility", camera=list(cam), visible_fraction=frac, rays=int(pts.shape[0]), faces=int(faces.shape[0]))
+
+
+def test_visibility_mask_multi_garment_matches_oracle():
+    """inference.py:285-316 semantics: several meshes in one scene (garment cylinder + an inner 'body' cylinder + a
+    skirt that hides part of both); a Gaussian is visible iff the first hit lies on its own garment or nothing is hit."""
+    dev = torch.device("cuda:0")
+    v0, f0, b0, p0 = _garment_scene(seed=3)
+    v1, f1 = gg.scenes.cylinder_mesh(n_around=60, n_along=20, radius=0.2, height=1.2, wrinkle_amp=0.0)      # body
+    v2, f2 = gg.scenes.cylinder_mesh(n_around=80, n_along=10, radius=0.5, height=0.4, wrinkle_amp=0.0)      # skirt
+    g = torch.Generator().manual_seed(9)
+    p1 = v1[f1].mean(1)
+    p2 = v2[f2].mean(1) + 0.3 * torch.randn(f2.shape[0], 3, generator=g) * 0          # on the surface
+    free = torch.tensor([[5.0, 5.0, 5.0], [0.0, 3.0, 0.0]])                            # rays that hit nothing
+    pts = torch.cat([p0, p1, p2, free])
+    gid = torch.cat([torch.zeros(p0.shape[0]), torch.ones(p1.shape[0]), torch.full((p2.shape[0],), 2.0),
+                     torch.zeros(2)]).to(torch.int32)
+    cam = torch.tensor([1.8, 0.9, 2.2])
+    vis = gg.visible_mask_multi(cam.to(dev), [(v0.to(dev), f0.to(dev)), (v1.to(dev), f1.to(dev)), (v2.to(dev), f2.to(dev))],
+                                pts.to(dev), gid.to(dev))
+    # oracle: concatenate the meshes the same way
+    verts = torch.cat([v0, v1, v2])
+    faces = torch.cat([f0, f1 + v0.shape[0], f2 + v0.shape[0] + v1.shape[0]])
+    tri_geom = torch.cat([torch.zeros(f0.shape[0]), torch.ones(f1.shape[0]), torch.full((f2.shape[0],), 2.0)]).to(torch.int32)
+    prim, _ = h.c_oracle.cast_rays_from_point(verts, faces, pts, cam)
+    ref = (tri_geom[prim.clamp_min(0).long()] == gid) | (prim < 0)
+    assert torch.equal(vis.cpu(), ref)
+    assert bool(ref[-2:].all())                                   # nothing hit -> kept (reference: geometry_ids >= num_gs)
+    assert not bool(ref[p0.shape[0]:p0.shape[0] + p1.shape[0]].any())   # the body is entirely behind garment 0
