@@ -19,7 +19,7 @@ from .rasterizer import (  # noqa: F401
     rasterize_gaussians,
     mark_visible,
 )
-from . import cameras, scenes  # noqa: F401
+from . import cameras, scenes, densify, ply_io  # noqa: F401
 from .mesh_binding import bind_to_mesh, FusedMeshBinding  # noqa: F401
 from .losses import photometric_loss  # noqa: F401
 from .visibility import cast_rays_from_point, visible_mask, visible_mask_multi  # noqa: F401

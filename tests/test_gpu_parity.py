@@ -983,3 +983,56 @@ def test_visibility_mask_multi_garment_matches_oracle():
     assert torch.equal(vis.cpu(), ref)
     assert bool(ref[-2:].all())                                   # nothing hit -> kept (reference: geometry_ids >= num_gs)
     assert not bool(ref[p0.shape[0]:p0.shape[0] + p1.shape[0]].any())   # the body is entirely behind garment 0
+
+
+# ------------------------------------------------------------------------------------ N4: densification on the device
+def test_densification_cycle_on_device_feeds_the_rasterizer():
+    """Row N4 end to end on the GPU: render -> backward -> the means2D side channel drives add_densification_stats ->
+    densify_and_prune (clone / split / prune with the keep-one-per-face rule, Adam moments carried along) -> the grown
+    model renders again through the fused mesh binding.  The same cycle with the same generator seed on a second copy
+    gives identical tensors (what makes replicated ranks stay in lock-step)."""
+    import numpy as np, os
+    from test_densify_cpu import Model, NAMES
+    from gaussian_garments_b200 import densify as D
+    dev = torch.device("cuda:0")
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "densify.npz"))
+    cam = gg.scenes.ring_cameras(4, width=256, height=192)[1].to(dev)
+    bg = torch.tensor([0.1, 0.2, 0.3], device=dev)
+
+    def render(m):
+        xyz, sc, ro = gg.FusedMeshBinding(m).world()
+        shs = torch.cat([m._features_dc, m._features_rest], dim=1)
+        S = h.dgr.GaussianRasterizationSettings(image_height=192, image_width=256, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy,
+                                                bg=bg, scale_modifier=1.0, viewmatrix=cam.world_view_transform,
+                                                projmatrix=cam.full_proj_transform, sh_degree=3, campos=cam.camera_center,
+                                                prefiltered=False, debug=False)
+        screenspace = torch.zeros_like(xyz, requires_grad=True) + 0
+        screenspace.retain_grad()
+        color, radii, _, _ = h.dgr.GaussianRasterizer(raster_settings=S)(
+            means3D=xyz, means2D=screenspace, shs=shs, colors_precomp=None, opacities=torch.sigmoid(m._opacity),
+            scales=sc, rotations=ro, cov3D_precomp=None)
+        return color, radii, screenspace
+
+    outs = []
+    for _ in range(2):
+        m = Model(z, "s0", device=dev)
+        m.mesh_v, m.mesh_f = m.mesh.v, m.mesh.f
+        m._scaling.data += 3.0                            # the golden model's splats are tiny at this camera distance
+        color, radii, screenspace = render(m)
+        (color - 0.5).abs().mean().backward()
+        assert float(screenspace.grad[:, :2].abs().max()) > 0
+        D.add_densification_stats(m, screenspace, radii > 0)
+        m.max_radii2D = torch.max(m.max_radii2D, radii.float())
+        n0 = m._xyz.shape[0]
+        thr = float((m.xyz_gradient_accum / m.denom.clamp_min(1)).median())
+        D.densify_and_prune(m, thr, 0.005, 2.0, 4000, generator=D.rank_consistent_generator(31359, 500, dev))
+        assert m._xyz.shape[0] > n0 and int(m.binding_counter.min()) >= 1
+        assert int(m.binding_counter.sum()) == m._xyz.shape[0] == m.binding.shape[0]
+        for k, a in NAMES.items():                        # Adam moments follow their rows
+            p = getattr(m, a)
+            assert m.optimizer.state[p]["exp_avg"].shape == p.shape
+        color2, radii2, _ = render(m)
+        assert radii2.shape[0] == m._xyz.shape[0] and torch.isfinite(color2).all()
+        outs.append({k: getattr(m, a).detach().clone() for k, a in NAMES.items()} | {"binding": m.binding.clone()})
+    for k in outs[0]:
+        assert torch.equal(outs[0][k], outs[1][k]), k
