@@ -8,8 +8,8 @@
 
 A "step" is one pass of the hot path over one view per GPU: GaussianRasterizer forward, L1 loss
 against a fixed random ground-truth image, backward into means3D/scales/rotations/opacities/SH,
-and -- for N > 1 -- one NCCL all-reduce of the flat gradient bucket (views are sharded one per
-GPU; weak scaling).  Rank 0 prints ONE JSON line.
+and -- for N > 1 -- the average of the flat gradient bucket over the ranks (in-switch multimem kernel, geometry block
+on the compute stream, SH block on a side stream; views are sharded one per GPU; weak scaling).  Rank 0 prints ONE JSON line.
 """
 from __future__ import annotations
 
@@ -55,6 +55,15 @@ def _best_thread_count(one_view) -> int:
             best, best_t = n, dt
     c_oracle.set_num_threads(best)
     return best
+
+
+def config_dict(args, world):
+    """The SAME dict in both arms (the driver compares them key by key)."""
+    return {"workload": WORKLOAD, "gaussians": args.gaussians, "width": args.width, "height": args.height,
+            "sh_degree": 3, "views_per_step": world, "parallelism": f"view-dp{world}", "cameras": N_CAMS,
+            "loss": "mean|image - gt| (lambda_dssim = 0)",
+            "l2": "flushed between timed steps (256 MiB write, outside the per-step CUDA events)",
+            "timing": "sum of per-step CUDA-event times, max over ranks"}
 
 
 def parse():
@@ -185,7 +194,7 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "gaussians": args.gaussians, "width": args.width, "height": args.height},
+            "config": config_dict(args, max(1, args.gpus)),
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                              "host_cores": _host_cores(),
                              "sample": f"{args.steps} views fwd+bwd of the same workload, oracle/gg_oracle.c with OpenMP "
@@ -219,7 +228,7 @@ def main():
     cams = [c.to(dev) for c in cams_cpu]
     params = [t.detach().clone().requires_grad_(True) for t in
               (st.means3D, st.scales, st.rotations, st.opacities, st.shs)]
-    bucket = GradBucket(params, world)
+    bucket = GradBucket(params, world, deferred=(4,))     # SH gradients: exchanged on the side stream (dist.py)
     gt_dev = [g.to(dev) for g in gts_cpu]
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     H, W = args.height, args.width
@@ -230,7 +239,7 @@ def main():
             viewmatrix=cam.world_view_transform, projmatrix=cam.full_proj_transform, sh_degree=st.sh_degree,
             campos=cam.camera_center, prefiltered=False, debug=False)
 
-    def step(i, gt, cam=None, collective=True):
+    def step(i, gt, cam=None, collective=True, drain=False):
         cam = cam if cam is not None else cams[(i * world + rank) % N_CAMS]
         means2D = torch.zeros_like(params[0], requires_grad=True)
         color, radii, depth, alpha = dgr.GaussianRasterizer(raster_settings=settings(cam))(
@@ -241,7 +250,9 @@ def main():
         loss.backward()
         if collective:
             bucket.all_reduce()
-        return loss
+            if drain:
+                bucket.wait()        # the deferred SH exchange normally hides behind the NEXT forward: the last timed
+        return loss                  # step has no successor, so it waits for it inside its own event window
 
     # ---------------- device-resident timing: `value` ----------------
     for i in range(args.warmup):
@@ -255,10 +266,13 @@ def main():
     _capi.launch_count(reset=True)
     sampler.start()
     t_wall0 = time.perf_counter()
+    host_s = 0.0
     for i in range(args.steps):
         flush_buf.fill_(i & 0xFF)                      # L2 flush between timed iterations (outside the events)
         ev[i][0].record()
-        step(i, gt_dev[i % 2])
+        th0 = time.perf_counter()
+        step(i, gt_dev[i % 2], drain=(i == args.steps - 1))
+        host_s += time.perf_counter() - th0
         ev[i][1].record()
     torch.cuda.synchronize()
     if world > 1:
@@ -340,6 +354,38 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * e_steps / float(t.item())
 
+    # ---------------- the exchange, checked and timed in isolation (all ranks; outside the timed regions) -------------
+    collective = None
+    if world > 1:
+        step(0, gt_dev[0], collective=False)                       # fresh local gradients in the bucket
+        bucket.adopt()
+        torch.cuda.synchronize()
+        local = bucket.flat.clone()
+        bucket.all_reduce()
+        chk = bucket.check_against_gather(local)                   # all-gather of the local buckets vs the exchanged one
+        ar_ms = []
+        for _ in range(5):
+            bucket.flat.copy_(local)
+            torch.cuda.synchronize()
+            dist.barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            bucket.all_reduce(overlap=False)
+            b.record()
+            torch.cuda.synchronize()
+            ar_ms.append(a.elapsed_time(b))
+        tt = torch.tensor([sorted(ar_ms)[len(ar_ms) // 2]], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        nbytes = bucket.numel * 4
+        collective = {"impl": bucket.impl, "nvls_error": bucket.nvls_error, "bytes": nbytes,
+                      "immediate_bytes": bucket.split * 4, "deferred_bytes": (bucket.numel - bucket.split) * 4,
+                      "ms_unoverlapped": float(tt.item()),
+                      "algbw_gbs": nbytes / (float(tt.item()) * 1e-3) / 1e9,
+                      "busbw_gbs": nbytes / (float(tt.item()) * 1e-3) / 1e9 * 2 * (world - 1) / world,
+                      "allreduce_check": chk,
+                      "note": "in the timed loop the deferred (SH) block runs on a side stream behind the next forward's "
+                              "projection / scan; ms_unoverlapped is both blocks back to back on one stream, barrier first"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -367,9 +413,11 @@ def main():
     K = int(sum(Ks) / len(Ks))
     gx, gy = (W + 15) // 16, (H + 15) // 16
     ab = algorithmic_bytes(args.gaussians, K, W * H, gx * gy)
-    traffic, ncu_issue = {}, {}
-    try:   # per-launch dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture (profiles/)
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))
+    traffic, ncu_issue, traffic_src = {}, {}, None
+    try:   # per-launch dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture (profiles/): STATIC
+        tpath = next(p for p in ("r2_ncu_traffic.json", "r1_ncu_traffic.json") if os.path.exists(os.path.join(ROOT, "profiles", p)))
+        traffic_src = f"static: profiles/{tpath} (ncu --set full capture of this command, not measured in this run)"
+        tj = json.load(open(os.path.join(ROOT, "profiles", tpath)))
         traffic = {k: int(v["traffic"]) for k, v in tj["kernels"].items()}
         ncu_issue = {k: v.get("ncu_issue_slot_pct") for k, v in tj["kernels"].items()}
     except Exception:
@@ -390,7 +438,7 @@ def main():
                 "note": "blend kernels are instruction-issue bound by construction (256*K pixel-Gaussian pairs >> their "
                         "bytes): ncu issue-slot utilisation 64-69 % at ~1-3 % DRAM (`ncu_issue_slot_pct`, from the committed "
                         "capture); the streaming kernels (preprocess_bwd, sh_color, photometric) carry the HBM claim",
-                "ncu_issue_slot_pct": ncu_issue.get(dom["kernel"]),
+                "ncu_issue_slot_pct": ncu_issue.get(dom["kernel"]), "traffic_source": traffic_src,
                 "kernels": kernels, "kernel_ms_sum": round(sum(k["ms"] for k in kernels), 4)}
 
     cpu_baseline = None
@@ -400,24 +448,30 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "gaussians": args.gaussians, "width": W, "height": H, "sh_degree": 3,
-                       "views_per_step": world, "parallelism": f"view-dp{world}", "cameras": N_CAMS,
-                       "l2": "flushed between timed steps (256 MiB write, outside the per-step CUDA events)",
-                       "timing": "sum of per-step CUDA-event times, max over ranks"},
+            "config": config_dict(args, world),
             "step_ms": {"p10": step_ms[len(step_ms) // 10], "median": step_ms[len(step_ms) // 2],
                         "p90": step_ms[(len(step_ms) * 9) // 10]},
-            "wall_s_timed_region_incl_flush": wall,
+            "wall_s_timed_region_incl_flush": wall, "host_ms_per_step": 1e3 * host_s / args.steps,
+            "forward_stats": dict(_rasterizer_stats()),
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "what": "pinned-host GT image + camera matrices copied H2D every step (on a copy stream, overlapping "
                             "the previous step's compute), public GaussianRasterizer API fwd + fused L1 + bwd, every step's "
                             "loss copied D2H (async, read one step later); wall clock, max over ranks", "steps": e_steps},
             "roofline": roofline}
+    if collective is not None:
+        line["collective"] = collective
+        line["allreduce_check"] = collective["allreduce_check"]
     if cpu_baseline is not None:
         line["cpu_baseline"] = cpu_baseline
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _rasterizer_stats():
+    from gaussian_garments_b200 import rasterizer
+    return rasterizer.STATS
 
 
 def _capi_last_K():

@@ -14,7 +14,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.environ.get("GG_RASTER_LIB") or os.path.join(CSRC, "libgg_raster.so")   # override: dev experiments
-SOURCES = ["project.cu", "binning.cu", "blend_fwd.cu", "blend_bwd.cu", "blend_bwd2.cu", "preprocess_bwd.cu", "mesh_binding.cu", "photometric.cu", "visibility.cu", "c_api.cu"]
+SOURCES = ["project.cu", "binning.cu", "blend_fwd.cu", "blend_bwd.cu", "blend_bwd2.cu", "preprocess_bwd.cu", "mesh_binding.cu", "photometric.cu", "visibility.cu", "allreduce.cu", "c_api.cu"]
 HEADERS = ["common.cuh", "mesh_binding_math.h", os.path.join("..", "..", "include", "gg_raster.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -122,6 +122,7 @@ def load():
         lib.gg_mesh_bind_backward_ex.argtypes = [C.c_int32] * 3 + [vp] * 17 + [i32, vp]
         lib.gg_cast_rays_workspace_bytes.argtypes = [C.c_int32, C.c_int32, P(sz), P(C.c_int64)]
         lib.gg_cast_rays_from_point.argtypes = [C.c_int32] * 3 + [vp] * 6 + [i64, C.c_int32, vp, vp, i32, vp]
+        lib.gg_nvls_allreduce_f32.argtypes = [vp, vp, C.c_int32, C.c_int32, i64, i64, C.c_float, C.c_int32, C.c_int32, i32, vp]
         lib.gg_photometric_workspace_bytes.argtypes = [C.c_int32, C.c_int32, P(sz)]
         lib.gg_photometric_forward.argtypes = [C.c_int32, C.c_int32, vp, vp, vp, vp, C.c_int32, i32, vp]
         lib.gg_photometric_backward.argtypes = [C.c_int32, C.c_int32, vp, vp, vp, vp, C.c_float, C.c_float, vp, vp, i32, vp]
@@ -135,7 +136,7 @@ def load():
                      "gg_mark_visible", "gg_debug_read_geom", "gg_debug_read_binning", "gg_kernel_timing", "gg_kernel_times",
                      "gg_mesh_bind_workspace_bytes", "gg_mesh_bind_forward", "gg_mesh_bind_backward",
                      "gg_mesh_bind_forward_ex", "gg_mesh_bind_backward_ex", "gg_cast_rays_workspace_bytes",
-                     "gg_cast_rays_from_point",
+                     "gg_cast_rays_from_point", "gg_nvls_allreduce_f32",
                      "gg_photometric_workspace_bytes", "gg_photometric_forward", "gg_photometric_backward"):
             getattr(lib, name).restype = C.c_int
         if lib.gg_abi_version() != 1:
@@ -157,7 +158,7 @@ EXPORTED_SYMBOLS = [
     "gg_kernel_timing",
     "gg_kernel_count", "gg_kernel_name", "gg_kernel_times", "gg_mesh_bind_workspace_bytes", "gg_mesh_bind_forward",
     "gg_mesh_bind_backward", "gg_mesh_bind_forward_ex", "gg_mesh_bind_backward_ex", "gg_cast_rays_workspace_bytes",
-    "gg_cast_rays_from_point", "gg_photometric_workspace_bytes", "gg_photometric_forward", "gg_photometric_backward",
+    "gg_cast_rays_from_point", "gg_nvls_allreduce_f32", "gg_photometric_workspace_bytes", "gg_photometric_forward", "gg_photometric_backward",
 ]
 
 

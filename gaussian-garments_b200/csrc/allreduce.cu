@@ -1,0 +1,86 @@
+// allreduce.cu -- in-switch (NVLS) average of the flat gradient bucket across the ranks of one NVSwitch domain.
+//
+// The only exchange on the path is the per-step sum of the per-view parameter gradients: one flat fp32
+// bucket (236 B x N Gaussians = 70.8 MB at cfg2) that every rank's preprocess-backward kernel has just written in
+// place (zero-copy grad sinks).  The bucket lives in symmetric memory that is also mapped behind ONE multicast address
+// (torch.distributed._symmetric_memory supplies allocation, rendezvous and the signal pads -- plumbing only), so the
+// reduction is a single kernel per rank with no staging buffers and no NCCL ring:
+//     rank r owns the r-th 1/world slice;  for every 16 bytes of it:
+//         v = multimem.ld_reduce.add.v4.f32 [mc + i]     the switch pulls the 16 B from all ranks and adds them
+//         v *= 1/world                                    (the averaging is fused here)
+//         multimem.st.v4.f32 [mc + i], v                  the switch writes the result into every rank's bucket
+// Per GPU ~ bytes/world in + bytes out per phase instead of 2 (world-1)/world x bytes through a ring, and the adds
+// happen in the switch.  Cross-rank ordering uses the symmetric-memory signal pads: every block exchanges one flag
+// with the same block of every peer on entry (all ranks' gradients are complete) and on exit (all results landed).
+// Two instances may be in flight on different streams (geometry block / SH block) -- they use disjoint pad channels.
+#include "common.cuh"
+
+namespace gg {
+
+constexpr int AR_THREADS = 512;
+
+__device__ __forceinline__ uint32_t cas_sys_relaxed(uint32_t* a, uint32_t cmp, uint32_t val) {
+    uint32_t old;
+    asm volatile("atom.global.relaxed.sys.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "l"(a), "r"(cmp), "r"(val) : "memory");
+    return old;
+}
+__device__ __forceinline__ uint32_t cas_sys_release(uint32_t* a, uint32_t cmp, uint32_t val) {
+    uint32_t old;
+    asm volatile("atom.global.release.sys.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "l"(a), "r"(cmp), "r"(val) : "memory");
+    return old;
+}
+__device__ __forceinline__ uint32_t cas_sys_acquire(uint32_t* a, uint32_t cmp, uint32_t val) {
+    uint32_t old;
+    asm volatile("atom.global.acquire.sys.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "l"(a), "r"(cmp), "r"(val) : "memory");
+    return old;
+}
+
+// One flag per (block, peer): thread t < world raises the flag in peer t's pad and waits for peer t's flag in ours.
+// Flags toggle 0 -> 1 (raise) -> 0 (consume), so the pads are ready for the next call without a reset.
+template <bool RELEASE_ACQUIRE>
+__device__ __forceinline__ void cross_rank_barrier(uint32_t* const* __restrict__ pads, int rank, int world, int slot0) {
+    if ((int)threadIdx.x < world) {
+        const int peer = threadIdx.x;
+        uint32_t* theirs = pads[peer] + slot0 + (int)blockIdx.x * world + rank;
+        uint32_t* mine = pads[rank] + slot0 + (int)blockIdx.x * world + peer;
+        if (RELEASE_ACQUIRE) {
+            while (cas_sys_release(theirs, 0u, 1u) != 0u) {}
+            while (cas_sys_acquire(mine, 1u, 0u) != 1u) {}
+        } else {
+            while (cas_sys_relaxed(theirs, 0u, 1u) != 0u) {}
+            while (cas_sys_relaxed(mine, 1u, 0u) != 1u) {}
+        }
+    }
+}
+
+__global__ void __launch_bounds__(AR_THREADS)
+nvls_allreduce_kernel(float* __restrict__ mc, uint32_t* const* __restrict__ pads, int rank, int world, int slot0,
+                      int64_t n_vec4, float scale) {
+    cross_rank_barrier<false>(pads, rank, world, slot0);      // every rank's producer kernels have finished
+    __syncthreads();
+    const int64_t per = (n_vec4 + world - 1) / world;
+    const int64_t beg = min((int64_t)rank * per, n_vec4), end = min(beg + per, n_vec4);
+    for (int64_t i = beg + (int64_t)blockIdx.x * AR_THREADS + threadIdx.x; i < end; i += (int64_t)gridDim.x * AR_THREADS) {
+        float4 v;
+        float* p = mc + 4 * i;
+        asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                     : "l"(p)
+                     : "memory");
+        v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+                     "f"(v.w)
+                     : "memory");
+    }
+    __syncthreads();
+    cross_rank_barrier<true>(pads, rank, world, slot0);       // every rank's slice has landed everywhere
+}
+
+int launch_nvls_allreduce(float* mc, uint32_t* const* pads, int rank, int world, int slot0, int64_t n_vec4, float scale,
+                          int blocks, cudaStream_t s) {
+    if (n_vec4 <= 0) return 0;
+    nvls_allreduce_kernel<<<blocks, AR_THREADS, 0, s>>>(mc, pads, rank, world, slot0, n_vec4, scale);
+    return 1;
+}
+
+}  // namespace gg

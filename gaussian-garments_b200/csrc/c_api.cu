@@ -484,6 +484,27 @@ int gg_cast_rays_from_point(int32_t num_vertices, int32_t num_faces, int32_t num
     return 0;
 }
 
+// ---- in-switch gradient average ------------------------------------------------------
+int gg_nvls_allreduce_f32(void* multicast_base, const void* signal_pads_dev, int32_t rank, int32_t world_size,
+                          int64_t elem_offset, int64_t elem_count, float scale, int32_t pad_slot0, int32_t num_blocks,
+                          int device, void* stream) {
+    if (!multicast_base || !signal_pads_dev) return fail(GG_E_BADARG, "NULL multicast pointer / signal pads");
+    if (world_size < 1 || rank < 0 || rank >= world_size) return fail(GG_E_BADARG, "bad rank / world_size");
+    if (world_size > 32) return fail(GG_E_BADARG, "world_size > 32 not supported");
+    if (elem_offset < 0 || elem_count < 0 || (elem_offset & 3) || (elem_count & 3))
+        return fail(GG_E_ALIGN, "elem_offset and elem_count must be multiples of 4 floats");
+    if (num_blocks < 1 || num_blocks > 148 || pad_slot0 < 0) return fail(GG_E_BADARG, "bad num_blocks / pad_slot0");
+    float* mc = reinterpret_cast<float*>(multicast_base) + elem_offset;
+    if (!aligned16(mc)) return fail(GG_E_ALIGN, "multicast pointer not 16-byte aligned");
+    GG_CUDA(cudaSetDevice(device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const gg_view* view = nullptr;
+    g_launches += launch_nvls_allreduce(mc, reinterpret_cast<uint32_t* const*>(signal_pads_dev), rank, world_size, pad_slot0,
+                                        elem_count / 4, scale, num_blocks, s);
+    GG_AFTER("nvls_allreduce_kernel");
+    return 0;
+}
+
 // ---- fused photometric loss --------------------------------------------------
 int gg_photometric_workspace_bytes(int32_t width, int32_t height, size_t* map_bytes) {
     if (width < 0 || height < 0) return fail(GG_E_BADARG, "negative size");

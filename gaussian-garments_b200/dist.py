@@ -1,40 +1,100 @@
-"""One-view-per-GPU data parallelism: a flat gradient bucket and its single all-reduce.
+"""One-view-per-GPU data parallelism: a flat gradient bucket and its per-step average over the ranks.
 
 The reference renders one view per optimiser step on one GPU (s2_registration.py:241-251,
 s3_appearance.py:107-124) and has no distributed code.  BASELINE.json's multi-GPU configs shard
 views one per rank; the only exchange on the path is the sum of the per-view parameter gradients.
 
-Design: all parameter gradients live in ONE contiguous fp32 buffer.  The rasterizer's
-backward kernel writes its outputs straight into views of that buffer (see `rasterizer.GradSink`),
-autograd's AccumulateGrad adopts those views as `.grad` without a copy, and a single
-`all_reduce(AVG)` over the flat buffer is the step's only collective -- no per-tensor launches, no
-staging copies.  NVSwitch gives every rank uniform bandwidth, so no topology tuning is needed.
+Design
+  * all parameter gradients live in ONE contiguous fp32 buffer.  The rasterizer's backward kernel writes its outputs
+    straight into views of that buffer (`rasterizer.GradSink`), autograd's AccumulateGrad adopts those views as
+    `.grad` without a copy -- no per-tensor launches, no staging copies.
+  * on an NVSwitch box the buffer is SYMMETRIC memory mapped behind one multicast address and the average is ONE
+    hand-written kernel per rank (csrc/allreduce.cu behind gg_nvls_allreduce_f32): multimem.ld_reduce lets the switch
+    add the ranks' copies, multimem.st lets it write the result back into every rank's bucket, 1/world fused in
+    between.  torch.distributed._symmetric_memory is used for allocation / rendezvous only.  Anything else (gloo on
+    CPU, no multicast support) falls back to the process group's all_reduce on the same ranges.
+  * the exchange is split where the next step's data dependence is: the geometry block (means / scales / rotations /
+    opacities, 13 MB at cfg2) is reduced on the compute stream; the `deferred` block (the SH coefficients, 57.6 MB)
+    is reduced on a high-priority side stream and only the next forward's SH->RGB kernel waits for it
+    (`rasterizer.COLOR_GATE`) -- projection, tile scan and instance emission of the next view do not read SH and
+    overlap with it.  Consumers of the deferred gradients call `wait()`.
 """
 
 from __future__ import annotations
 
-from typing import List, Sequence
+import ctypes as C
+from typing import List, Optional, Sequence
 
 import torch
 import torch.distributed as dist
 
 
 class GradBucket:
-    """Flat fp32 gradient storage for `params` + its all-reduce."""
+    """Flat fp32 gradient storage for `params` + its per-step average over `world_size` ranks."""
 
-    def __init__(self, params: Sequence[torch.Tensor], world_size: int = 1, register: bool = True):
+    def __init__(self, params: Sequence[torch.Tensor], world_size: int = 1, register: bool = True,
+                 deferred: Sequence[int] = (), symmetric: Optional[bool] = None, group=None):
         self.params: List[torch.Tensor] = list(params)
         self.world = int(world_size)
+        self.group = group
         dev = self.params[0].device
-        offs, total = [], 0
-        for p in self.params:
-            offs.append(total)
-            total += (p.numel() + 63) // 64 * 64          # keep every view 256-byte aligned
+        self.device = dev
+        # layout: immediate block first, deferred block last; every view 256-byte aligned
+        self.deferred = tuple(sorted(set(int(i) for i in deferred)))
+        order = [i for i in range(len(self.params)) if i not in self.deferred] + list(self.deferred)
+        offs, total = [0] * len(self.params), 0
+        self.split = None
+        for i in order:
+            if i in self.deferred and self.split is None:
+                self.split = total
+            offs[i] = total
+            total += (self.params[i].numel() + 63) // 64 * 64
+        if self.split is None:
+            self.split = total
         self.offsets = offs
-        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
         self.numel = total
+        self.impl = "none" if self.world <= 1 else "process_group"
+        self.nvls_error = None
+        self.flat = None
+        self._hdl = None
+        want_symm = symmetric if symmetric is not None else (self.world > 1 and dev.type == "cuda")
+        if want_symm and self.world > 1 and dist.is_initialized() and dist.get_backend(group) == "nccl":
+            try:
+                self._setup_symmetric(total, dev)
+            except Exception as e:           # no multicast support / symmetric memory unavailable: process-group path
+                self.nvls_error = f"{type(e).__name__}: {e}"
+                self.flat = None
+        if self.flat is None:
+            self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.comm_stream = None
+        self.late_done = None
+        if dev.type == "cuda" and self.world > 1 and self.split < total:
+            self.comm_stream = torch.cuda.Stream(device=dev, priority=-1)
+            self.late_done = torch.cuda.Event()
         if register:
             self.register()
+
+    # -- symmetric memory / multicast set-up (plumbing) -------------------------------------------------
+    def _setup_symmetric(self, total, dev):
+        import torch.distributed._symmetric_memory as symm_mem
+        flat = symm_mem.empty(total, dtype=torch.float32, device=dev)
+        flat.zero_()
+        grp = self.group if self.group is not None else dist.group.WORLD
+        hdl = symm_mem.rendezvous(flat, grp)
+        mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
+        if mc == 0:
+            raise RuntimeError("symmetric memory has no multicast (NVLS) mapping on this system")
+        self._hdl = hdl
+        self._mc_ptr = mc
+        self._pads_dev = int(hdl.signal_pad_ptrs_dev)
+        pad_words = int(hdl.signal_pad_size) // 4
+        blocks = max(2, min(72, pad_words // self.world))
+        self._blocks = (max(1, blocks // 3), max(1, blocks - blocks // 3))      # (immediate, deferred)
+        self._slot0 = (0, self._blocks[0] * self.world)
+        self.flat = flat
+        self.impl = "nvls_multimem"
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=self.group)
 
     # -- zero-copy hand-off to the rasterizer's backward ------------------------------------
     def register(self):
@@ -77,16 +137,67 @@ class GradBucket:
                 v.copy_(p.grad)
                 p.grad = v
 
-    def all_reduce(self):
-        """The step's single collective: mean of the flat bucket over ranks."""
+    # -- the exchange -------------------------------------------------------------------------
+    def _reduce_range(self, a: int, b: int, which: int):
+        """Average flat[a:b] over the ranks on the CURRENT stream."""
+        if b <= a:
+            return
+        if self.impl == "nvls_multimem":
+            from . import _capi
+            lib = _capi.load()
+            di = self.device.index if self.device.index is not None else torch.cuda.current_device()
+            sp = torch.cuda.current_stream(self.device).cuda_stream
+            _capi.check(lib.gg_nvls_allreduce_f32(self._mc_ptr, self._pads_dev, dist.get_rank(self.group), self.world, a,
+                                                  b - a, 1.0 / self.world, self._slot0[which], self._blocks[which], di, sp),
+                        "gg_nvls_allreduce_f32")
+            return
+        seg = self.flat[a:b]
+        if dist.get_backend(self.group) == "nccl":
+            dist.all_reduce(seg, op=dist.ReduceOp.AVG, group=self.group)
+        else:  # gloo (CPU tests): no AVG
+            dist.all_reduce(seg, op=dist.ReduceOp.SUM, group=self.group)
+            seg.div_(self.world)
+
+    def all_reduce(self, overlap: bool = True):
+        """The step's exchange: mean of the flat bucket over ranks.  The immediate block is reduced on the current
+        stream; the deferred block on the side stream (its completion gates the next forward's colour kernel)."""
         if self.world <= 1 or not dist.is_initialized():
             return
         self.adopt()
-        if dist.get_backend() == "nccl":
-            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG)
-        else:  # gloo (CPU tests): no AVG
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
-            self.flat.div_(self.world)
+        self._reduce_range(0, self.split, 0)
+        if self.split >= self.numel:
+            return
+        if self.comm_stream is None or not overlap:
+            self._reduce_range(self.split, self.numel, 1)
+            return
+        cur = torch.cuda.current_stream(self.device)
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        self.comm_stream.wait_event(ready)
+        with torch.cuda.stream(self.comm_stream):
+            self._reduce_range(self.split, self.numel, 1)
+            self.late_done.record(self.comm_stream)
+        from . import rasterizer
+        di = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        rasterizer.COLOR_GATE[di] = self.late_done          # next forward: SH -> RGB waits, projection/binning do not
+
+    def wait(self):
+        """Make the current stream wait for the deferred block (call before consuming those gradients)."""
+        if self.late_done is not None and self.comm_stream is not None:
+            torch.cuda.current_stream(self.device).wait_event(self.late_done)
+
+    def check_against_gather(self, local_copy: torch.Tensor) -> dict:
+        """Diagnostics (outside any timed region): all-gather every rank's LOCAL bucket (`local_copy`, taken before
+        all_reduce) and compare its mean with what the exchange left in the bucket."""
+        self.wait()
+        torch.cuda.synchronize(self.device) if self.device.type == "cuda" else None
+        parts = [torch.empty_like(local_copy) for _ in range(self.world)]
+        dist.all_gather(parts, local_copy.contiguous(), group=self.group)
+        mean = torch.stack(parts).double().mean(0)
+        diff = (self.flat.double() - mean).abs().max()
+        scale = mean.abs().max().clamp_min(1e-30)
+        return {"impl": self.impl, "max_abs_err": float(diff), "rel_err": float(diff / scale), "elements": int(self.numel),
+                "ok": bool(float(diff / scale) <= 1e-6)}
 
 
 def shard_views(num_views: int, rank: int, world: int) -> List[int]:

@@ -50,6 +50,9 @@ _tls = threading.local()
 LAST_NUM_RENDERED = 0   # K of the most recent forward (bench/diagnostics)
 STATS = {"forwards": 0, "hinted": 0, "overflow_retries": 0}
 DEBUG_CAPTURE = None    # tests set this to a dict: the next forward leaves its binning workspaces in it
+# device index -> CUDA event the SH -> RGB kernel must wait for (dist.GradBucket: the deferred SH-gradient exchange of the
+# previous step runs on a side stream while this forward's projection / tile scan are already executing)
+COLOR_GATE = {}
 
 
 class GradSink:
@@ -195,6 +198,9 @@ class _RasterizeGaussians(torch.autograd.Function):
                                 "gg_forward_project")
                     k_ready = torch.cuda.Event()
                     k_ready.record(stream)
+                    gate = COLOR_GATE.get(di)
+                    if gate is not None:
+                        stream.wait_event(gate)
                     _capi.check(lib.gg_forward_color(C.byref(view), C.byref(inputs), geom_ws.data_ptr(),
                                                      radii.data_ptr(), di, sp), "gg_forward_color")
                     hkey = (di, N, W, H)

@@ -187,6 +187,19 @@ int gg_cast_rays_from_point(int32_t num_vertices, int32_t num_faces, int32_t num
                             void* ws, int64_t list_capacity, int32_t force_bruteforce, int32_t* primitive_ids,
                             float* t_hit, int device, void* stream);
 
+/* ---- in-switch (NVLS) average of the gradient bucket (multi-GPU row 8e) --------------------------------
+ * The reference has no distributed code; BASELINE.json's multi-GPU configs shard views one per GPU and exchange only
+ * the per-step sum of the parameter gradients.  `multicast_base` is the multicast (multimem) address of a symmetric
+ * fp32 buffer every rank has written its local gradients into (the flat bucket the backward kernel's outputs alias);
+ * on return -- stream-ordered -- elements [elem_offset, elem_offset + elem_count) of EVERY rank's buffer hold
+ * scale * (sum over ranks).  One kernel per rank: multimem.ld_reduce (the switch adds) + multimem.st (the switch
+ * broadcasts); rank r reduces the r-th 1/world slice.  signal_pads_dev: device array of world_size pointers to the
+ * ranks' uint32 signal pads (zero-initialised; num_blocks * world_size words from pad_slot0 are used -- give concurrent
+ * calls on different streams disjoint ranges).  All ranks must call with identical arguments, in the same order.   */
+int gg_nvls_allreduce_f32(void* multicast_base, const void* signal_pads_dev, int32_t rank, int32_t world_size,
+                          int64_t elem_offset, int64_t elem_count, float scale, int32_t pad_slot0, int32_t num_blocks,
+                          int device, void* stream);
+
 /* ---- fused photometric loss ("next" row N2) -------------------------------------------------
  * Replaces l1_loss(image, gt, mask) and ssim(image, gt, mask) of /root/reference/utils/loss_utils.py:17-69
  * as used at s2_registration.py:259-260 / s3_appearance.py:132-133.  image, gt: [3,H,W]; mask: [1,H,W]

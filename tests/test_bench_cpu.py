@@ -49,3 +49,15 @@ def test_algorithmic_bytes_match_design_table():
     assert ab["preprocess_bwd"] == (84 + 192) * N + (56 + 192) * N
     assert set(ab) >= {"project", "tile_scan", "sh_color", "emit", "sort_pack", "blend_fwd", "blend_bwd",
                        "preprocess_bwd", "photometric_fwd", "photometric_bwd"}
+
+
+def test_both_arms_report_the_same_config_dict():
+    """the driver compares the two arms' `config` dicts key by key -- one function builds both."""
+    sys.path.insert(0, ROOT)
+    import argparse
+    import bench
+    a = argparse.Namespace(gaussians=300_000, width=1920, height=1080, gpus=4)
+    ours, ref = bench.config_dict(a, 4), bench.config_dict(a, max(1, a.gpus))
+    assert ours == ref and ours["workload"] == bench.WORKLOAD and ours["views_per_step"] == 4
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    assert src.count('"config": config_dict(') == 2

@@ -75,6 +75,42 @@ def test_two_rank_bucket_allreduce_equals_single_rank_mean(tmp_path):
         assert torch.allclose(r0[s], expect, atol=1e-6)
 
 
+def _split_worker(rank, world, port, out_dir):
+    sys.path.insert(0, h.ROOT)
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    params = [torch.zeros(20, 3, requires_grad=True), torch.zeros(20, 16, 3, requires_grad=True),
+              torch.zeros(20, 1, requires_grad=True)]
+    bucket = GradBucket(params, world, deferred=(1,))          # the SH block is exchanged separately (side stream on GPU)
+    assert bucket.impl == "process_group" and bucket.offsets[1] == bucket.split > bucket.offsets[2] > bucket.offsets[0] == 0
+    bucket.zero()
+    for i, g in enumerate(_fake_view_grads(params, rank)):
+        bucket.view(i).copy_(g)
+        params[i].grad = bucket.view(i)
+    local = bucket.flat.clone()
+    bucket.all_reduce()
+    bucket.wait()
+    chk = bucket.check_against_gather(local)
+    assert chk["ok"] and chk["elements"] == bucket.numel, chk
+    torch.save(bucket.flat.clone(), os.path.join(out_dir, f"split{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_split_exchange_immediate_and_deferred_blocks_equal_the_mean(tmp_path):
+    port = _free_port()
+    mp.spawn(_split_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    a, b = torch.load(tmp_path / "split0.pt"), torch.load(tmp_path / "split1.pt")
+    assert torch.equal(a, b)
+    params = [torch.zeros(20, 3), torch.zeros(20, 16, 3), torch.zeros(20, 1)]
+    ref = GradBucket([p.requires_grad_(True) for p in params], 1, register=False, deferred=(1,))
+    expect = torch.zeros_like(ref.flat)
+    for r in range(2):
+        for i, g in enumerate(_fake_view_grads(params, r)):
+            o = ref.offsets[i]
+            expect[o:o + g.numel()] += g.reshape(-1) / 2
+    assert torch.allclose(a, expect, atol=1e-6)
+
+
 def test_shard_views_partitions_all_views():
     for world in (1, 2, 4, 8):
         seen = sorted(v for r in range(world) for v in shard_views(32, r, world))
