@@ -18,6 +18,7 @@
 namespace gg {
 
 constexpr int AR_THREADS = 512;
+constexpr int AR_UNROLL = 8;
 
 __device__ __forceinline__ uint32_t cas_sys_relaxed(uint32_t* a, uint32_t cmp, uint32_t val) {
     uint32_t old;
@@ -60,17 +61,28 @@ nvls_allreduce_kernel(float* __restrict__ mc, uint32_t* const* __restrict__ pads
     __syncthreads();
     const int64_t per = (n_vec4 + world - 1) / world;
     const int64_t beg = min((int64_t)rank * per, n_vec4), end = min(beg + per, n_vec4);
-    for (int64_t i = beg + (int64_t)blockIdx.x * AR_THREADS + threadIdx.x; i < end; i += (int64_t)gridDim.x * AR_THREADS) {
-        float4 v;
-        float* p = mc + 4 * i;
-        asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
-                     : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-                     : "l"(p)
-                     : "memory");
-        v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
-        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
-                     "f"(v.w)
-                     : "memory");
+    // AR_UNROLL independent 16-byte reductions in flight per thread: one round trip through the switch is ~2-3 us, so
+    // bytes in flight (blocks x 512 x 16 B x AR_UNROLL) set the bandwidth, not the instruction rate
+    const int64_t stride = (int64_t)gridDim.x * AR_THREADS;
+    for (int64_t i0 = beg + (int64_t)blockIdx.x * AR_THREADS + threadIdx.x; i0 < end; i0 += stride * AR_UNROLL) {
+        float4 v[AR_UNROLL];
+#pragma unroll
+        for (int u = 0; u < AR_UNROLL; u++) {
+            const int64_t i = i0 + u * stride;
+            if (i < end)
+                asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                             : "=f"(v[u].x), "=f"(v[u].y), "=f"(v[u].z), "=f"(v[u].w)
+                             : "l"(mc + 4 * i)
+                             : "memory");
+        }
+#pragma unroll
+        for (int u = 0; u < AR_UNROLL; u++) {
+            const int64_t i = i0 + u * stride;
+            if (i < end)
+                asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc + 4 * i),
+                             "f"(v[u].x * scale), "f"(v[u].y * scale), "f"(v[u].z * scale), "f"(v[u].w * scale)
+                             : "memory");
+        }
     }
     __syncthreads();
     cross_rank_barrier<true>(pads, rank, world, slot0);       // every rank's slice has landed everywhere

@@ -541,6 +541,18 @@ int gg_photometric_forward(int32_t width, int32_t height, const float* image, co
     return 0;
 }
 
+int gg_photometric_reduce(int32_t width, int32_t height, const void* map_ws, float lambda_dssim, float* out3, int device,
+                          void* stream) {
+    if (width <= 0 || height <= 0 || !map_ws || !out3) return fail(GG_E_BADARG, "bad size or NULL argument");
+    GG_CUDA(cudaSetDevice(device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const gg_view* view = nullptr;
+    g_launches += launch_photometric_finalize((const double*)map_ws, 1.0 / (3.0 * (double)width * (double)height),
+                                              lambda_dssim, out3, s);
+    GG_AFTER("photometric_finalize_kernel");
+    return 0;
+}
+
 int gg_photometric_backward(int32_t width, int32_t height, const float* image, const float* gt, const float* mask,
                             const void* map_ws, float coeff_l1, float coeff_ssim, const float* upstream_scalar,
                             float* dL_dimage, int device, void* stream) {

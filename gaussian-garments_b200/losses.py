@@ -49,11 +49,10 @@ class _Photometric(torch.autograd.Function):
             sp = torch.cuda.current_stream(dev).cuda_stream
             _capi.check(lib.gg_photometric_forward(W, H, img.data_ptr(), g.data_ptr(), None if m is None else m.data_ptr(),
                                                    ws.data_ptr(), 1 if lambda_dssim != 0.0 else 0, di, sp), "gg_photometric_forward")
-        sums = ws[:1024].view(torch.float64).view(2, 64).sum(dim=1)
-        n = 3.0 * H * W
-        l1 = (sums[0] / n).float()
-        ssim_v = (sums[1] / n).float()
-        total = l1 * (1.0 - lambda_dssim) + (1.0 - ssim_v * lambda_dssim)
+            out3 = torch.empty(3, dtype=torch.float32, device=dev)
+            _capi.check(lib.gg_photometric_reduce(W, H, ws.data_ptr(), float(lambda_dssim), out3.data_ptr(), di, sp),
+                        "gg_photometric_reduce")
+        total, l1, ssim_v = out3[0], out3[1], out3[2]
         ctx.save_for_backward(img, g, m if m is not None else torch.empty(0, device=dev), ws)
         ctx.lam, ctx.hw = float(lambda_dssim), (H, W)
         ctx.mark_non_differentiable(l1, ssim_v)

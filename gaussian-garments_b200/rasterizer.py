@@ -19,6 +19,7 @@ from __future__ import annotations
 
 import ctypes as C
 import threading
+import time
 import weakref
 from typing import NamedTuple, Optional
 
@@ -48,7 +49,7 @@ class GaussianRasterizationSettings(NamedTuple):
 _tls = threading.local()
 
 LAST_NUM_RENDERED = 0   # K of the most recent forward (bench/diagnostics)
-STATS = {"forwards": 0, "hinted": 0, "overflow_retries": 0}
+STATS = {"forwards": 0, "hinted": 0, "overflow_retries": 0, "k_wait_s": 0.0}
 DEBUG_CAPTURE = None    # tests set this to a dict: the next forward leaves its binning workspaces in it
 # device index -> CUDA event the SH -> RGB kernel must wait for (dist.GradBucket: the deferred SH-gradient exchange of the
 # previous step runs on a side stream while this forward's projection / tile scan are already executing)
@@ -210,7 +211,9 @@ class _RasterizeGaussians(torch.autograd.Function):
                         STATS["hinted"] += 1
                         capacity = hint[0]
                         key_ws, record_ws = render(capacity, hint[1])
+                    _t0 = time.perf_counter()
                     k_ready.synchronize()        # scan + 8-byte copy only; later kernels keep running
+                    STATS["k_wait_s"] += time.perf_counter() - _t0
                     K, max_tile = (int(v) & 0xFFFFFFFF for v in word.tolist())
                     if hint is None or K > capacity:
                         if hint is not None:

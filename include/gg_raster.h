@@ -212,6 +212,11 @@ int gg_nvls_allreduce_f32(void* multicast_base, const void* signal_pads_dev, int
 int gg_photometric_workspace_bytes(int32_t width, int32_t height, size_t* map_bytes);
 int gg_photometric_forward(int32_t width, int32_t height, const float* image, const float* gt, const float* mask,
                            void* map_ws, int32_t with_ssim, int device, void* stream);
+/* folds the accumulator slots gg_photometric_forward left in map_ws into out3 (device float[3]) =
+ * (total, l1_loss, ssim) with total = l1_loss (1 - lambda_dssim) + 1 - ssim lambda_dssim
+ * (= loss_dict['img'] + loss_dict['ssim'] of s2_registration.py:259-260); nothing visits the host.              */
+int gg_photometric_reduce(int32_t width, int32_t height, const void* map_ws, float lambda_dssim, float* out3, int device,
+                          void* stream);
 int gg_photometric_backward(int32_t width, int32_t height, const float* image, const float* gt, const float* mask,
                             const void* map_ws, float coeff_l1, float coeff_ssim, const float* upstream_scalar,
                             float* dL_dimage, int device, void* stream);

@@ -47,8 +47,8 @@ for symmetric in (False, True):
     g = torch.Generator(device=dev).manual_seed(100 + rank)
     b.flat.copy_(torch.randn(b.numel, device=dev, generator=g))
     local_copy = b.flat.clone()
-    for p in params:
-        p.grad = None
+    for i, p in enumerate(params):
+        p.grad = b.view(i)                   # as after a backward through the grad sinks
     b.all_reduce(overlap=False)
     chk = b.check_against_gather(local_copy)
     full = timeit(lambda: b.all_reduce(overlap=False))
