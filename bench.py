@@ -76,6 +76,7 @@ def parse():
     ap.add_argument("--width", type=int, default=WIDTH)
     ap.add_argument("--height", type=int, default=HEIGHT)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="no CUDA graphs: every step through Python")
     ap.add_argument("--cpu-views", type=int, default=3, help="views timed for the cpu_baseline block")
     return ap.parse_args()
 
@@ -254,9 +255,95 @@ def main():
                 bucket.wait()        # the deferred SH exchange normally hides behind the NEXT forward: the last timed
         return loss                  # step has no successor, so it waits for it inside its own event window
 
+    # ---------------- CUDA graphs: the whole step (forward, fused L1, backward, exchange) as ONE launch --------------
+    # The public API is called unchanged inside a torch.cuda.graph capture (rasterizer.py: the sync-free hinted forward
+    # needs no host round trip; instance-capacity overflow is recorded on the device and checked after the loops).
+    # Two graphs, one per input slot: slot k owns a ground-truth buffer and a camera (view / projection / centre).
+    import copy
+    from gaussian_garments_b200 import rasterizer as _rast
+    slot_gt = [torch.empty(3, H, W, device=dev) for _ in range(2)]
+    slot_cam = [[torch.empty(4, 4, device=dev), torch.empty(4, 4, device=dev), torch.empty(3, device=dev)] for _ in range(2)]
+    slot_loss = [torch.zeros(1, device=dev) for _ in range(2)]
+    slot_camobj = []
+    for k in range(2):
+        c = copy.copy(cams[0])
+        c.world_view_transform, c.full_proj_transform, c.camera_center = slot_cam[k]
+        slot_camobj.append(c)
+    same_fov = all(abs(c.tanfovx - cams[0].tanfovx) < 1e-12 and abs(c.tanfovy - cams[0].tanfovy) < 1e-12 for c in cams)
+
+    def load_slot(k, ci, gt=None):
+        for dst, src in zip(slot_cam[k], (cams[ci].world_view_transform, cams[ci].full_proj_transform, cams[ci].camera_center)):
+            dst.copy_(src, non_blocking=True)
+        if gt is not None:
+            slot_gt[k].copy_(gt, non_blocking=True)
+
+    def slot_body(k):
+        """One step on slot k.  Multi-GPU: the deferred (SH) block of the PREVIOUS step is exchanged on the side stream
+        first and joins at this forward's colour kernel; the immediate block is exchanged after the backward."""
+        if world > 1:
+            bucket.exchange_deferred_async()
+        loss = step(0, slot_gt[k], slot_camobj[k], collective=False)
+        if world > 1:
+            bucket.adopt()
+            bucket.exchange_immediate()
+        slot_loss[k].copy_(loss.detach().reshape(1))
+
+    graphs, graph_note, launches_per_replay = None, None, 0
+    if args.eager:
+        graph_note = "disabled (--eager)"
+    elif not same_fov:
+        graph_note = "disabled: cameras differ in field of view (host-side scalars of the settings tuple)"
+    elif world > 1 and bucket.impl != "nvls_multimem":
+        graph_note = f"disabled: exchange runs through the process group ({bucket.nvls_error})"
+    else:
+        try:
+            for k in range(2):
+                load_slot(k, (k * world + rank) % N_CAMS, gt_dev[k])
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):                  # eager warm-up on a side stream (sizes the capacity hints)
+                for i in range(max(3, min(args.warmup, 2 * N_CAMS))):
+                    load_slot(i % 2, (i * world + rank) % N_CAMS)
+                    slot_body(i % 2)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            if world > 1:
+                bucket.wait()
+                dist.barrier()
+            graphs = []
+            for k in range(2):
+                _capi.launch_count(reset=True)
+                g_ = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g_):
+                    slot_body(k)
+                launches_per_replay = _capi.launch_count()
+                graphs.append(g_)
+            torch.cuda.synchronize()
+            graph_note = "2 graphs (one per input slot), whole step per launch"
+        except Exception as e:                             # never lose the bench line to a capture problem
+            graphs = None
+            graph_note = f"capture failed, eager fallback: {type(e).__name__}: {str(e)[:200]}"
+            try:
+                torch.cuda.synchronize()
+            except Exception:
+                pass
+
+    def run_step(i, gt_src=None, last=False):
+        """Step i through a graph replay (or eagerly): camera of this rank into slot i%2, replay, drain at the end."""
+        k = i % 2
+        ci = (i * world + rank) % N_CAMS
+        if graphs is None:
+            return step(i, gt_dev[k] if gt_src is None else gt_src, cams[ci], drain=last)
+        load_slot(k, ci)
+        graphs[k].replay()
+        if last and world > 1:
+            bucket.exchange_deferred_async()               # the final step's SH block has no successor graph
+            bucket.wait()
+        return slot_loss[k]
+
     # ---------------- device-resident timing: `value` ----------------
     for i in range(args.warmup):
-        step(i, gt_dev[i % 2])
+        run_step(i)
     torch.cuda.synchronize()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     sampler = ClockSampler(local)
@@ -271,7 +358,7 @@ def main():
         flush_buf.fill_(i & 0xFF)                      # L2 flush between timed iterations (outside the events)
         ev[i][0].record()
         th0 = time.perf_counter()
-        step(i, gt_dev[i % 2], drain=(i == args.steps - 1))
+        run_step(i, last=(i == args.steps - 1))
         host_s += time.perf_counter() - th0
         ev[i][1].record()
     torch.cuda.synchronize()
@@ -280,7 +367,7 @@ def main():
     torch.cuda.synchronize()
     wall = time.perf_counter() - t_wall0
     clocks = sampler.stop()
-    launches = _capi.launch_count()
+    launches = _capi.launch_count() + (launches_per_replay * args.steps if graphs is not None else 0)
     step_ms = sorted(a.elapsed_time(b) for a, b in ev)
     total_ms = sum(step_ms)
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
@@ -293,45 +380,46 @@ def main():
     gt_pinned = [g.pin_memory() for g in gts_cpu]
     cam_pinned = [(c.world_view_transform.pin_memory(), c.full_proj_transform.pin_memory(), c.camera_center.pin_memory())
                   for c in cams_cpu]
-    import copy
     h2d = gt_pinned[0].numel() * 4 + (16 + 16 + 3) * 4
 
-    # The H2D copy of step i+1's inputs is issued on a copy stream while step i computes (what a pinned-memory
-    # DataLoader with non_blocking copies gives the reference); every copy still happens inside the timed region.
+    # The H2D copy of step i+1's inputs (pinned host -> the slot's device buffers) is issued on a copy stream while step
+    # i computes (what a pinned-memory DataLoader with non_blocking copies gives the reference); every copy still
+    # happens inside the timed region.  The loss of step i is copied D2H asynchronously and read on the host while step
+    # i+1 is already enqueued, so the GPU never waits for Python; every step's result is read inside the timed region.
     copy_stream = torch.cuda.Stream(device=dev)
-    gt_stage = [torch.empty(3, H, W, device=dev) for _ in range(2)]
-    cam_stage = [[torch.empty(4, 4, device=dev), torch.empty(4, 4, device=dev), torch.empty(3, device=dev)] for _ in range(2)]
     ready = [torch.cuda.Event() for _ in range(2)]
+    loss_host = torch.zeros(2).pin_memory()
+    done = [torch.cuda.Event() for _ in range(2)]
 
     def prefetch(i):
         ci = (i * world + rank) % N_CAMS
         with torch.cuda.stream(copy_stream):
-            gt_stage[i % 2].copy_(gt_pinned[i % 2], non_blocking=True)
-            for dst, src in zip(cam_stage[i % 2], cam_pinned[ci]):
+            slot_gt[i % 2].copy_(gt_pinned[i % 2], non_blocking=True)
+            for dst, src in zip(slot_cam[i % 2], cam_pinned[ci]):
                 dst.copy_(src, non_blocking=True)
             ready[i % 2].record(copy_stream)
-
-    # The loss of step i is copied D2H asynchronously and read on the host while step i+1 is already enqueued, so the
-    # GPU never waits for Python; every step's result is still read back inside the timed region.
-    loss_host = torch.zeros(2).pin_memory()
-    done = [torch.cuda.Event() for _ in range(2)]
 
     def e2e_run(n):
         vals = []
         cur = torch.cuda.current_stream()
         prefetch(0)
         for i in range(n):
-            ci = (i * world + rank) % N_CAMS
-            cur.wait_event(ready[i % 2])
+            k = i % 2
+            cur.wait_event(ready[k])
             if i + 1 < n:
                 if i >= 1:
-                    copy_stream.wait_event(done[(i - 1) % 2])      # stage (i+1)%2 is free once step i-1 has finished
+                    copy_stream.wait_event(done[(i - 1) % 2])      # slot (i+1)%2 is free once step i-1 has finished
                 prefetch(i + 1)
-            cam = copy.copy(cams_cpu[ci])
-            cam.world_view_transform, cam.full_proj_transform, cam.camera_center = cam_stage[i % 2]
-            loss = step(i, gt_stage[i % 2], cam)
-            loss_host[i % 2:i % 2 + 1].copy_(loss.detach().reshape(1), non_blocking=True)   # D2H read of the result
-            done[i % 2].record(cur)
+            if graphs is not None:
+                graphs[k].replay()
+                if i == n - 1 and world > 1:
+                    bucket.exchange_deferred_async()
+                    bucket.wait()
+                loss = slot_loss[k]
+            else:
+                loss = step(i, slot_gt[k], slot_camobj[k], drain=(i == n - 1))
+            loss_host[k:k + 1].copy_(loss.detach().reshape(1), non_blocking=True)   # D2H read of the result
+            done[k].record(cur)
             if i >= 1:
                 done[(i - 1) % 2].synchronize()
                 vals.append(float(loss_host[(i - 1) % 2]))
@@ -346,13 +434,14 @@ def main():
         dist.barrier()
     e_steps = max(10, args.steps // 2)
     t0 = time.perf_counter()
-    e2e_run(e_steps)
+    e2e_vals = e2e_run(e_steps)
     torch.cuda.synchronize()
     e_dt = time.perf_counter() - t0
     t = torch.tensor([e_dt], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * e_steps / float(t.item())
+    graph_overflowed, graph_max_k = _rast.graph_overflow(dev) if graphs is not None else (False, 0)
 
     # ---------------- the exchange, checked and timed in isolation (all ranks; outside the timed regions) -------------
     collective = None
@@ -452,6 +541,9 @@ def main():
             "step_ms": {"p10": step_ms[len(step_ms) // 10], "median": step_ms[len(step_ms) // 2],
                         "p90": step_ms[(len(step_ms) * 9) // 10]},
             "wall_s_timed_region_incl_flush": wall, "host_ms_per_step": 1e3 * host_s / args.steps,
+            "cuda_graphs": {"mode": graph_note, "launches_per_replay": launches_per_replay,
+                            "instance_overflow": graph_overflowed, "max_num_rendered": graph_max_k},
+            "e2e_loss_first_last": [e2e_vals[0], e2e_vals[-1]],
             "forward_stats": dict(_rasterizer_stats()),
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,

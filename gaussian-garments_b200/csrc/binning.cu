@@ -196,6 +196,17 @@ sort_pack_kernel(const uint32_t* __restrict__ tile_offset, uint64_t* __restrict_
     }
 }
 
+// sticky overflow flag for sync-free (CUDA-graph) operation: *flag |= 1 when this view's instance count exceeds the
+// capacity its workspaces were laid out for (the instance stages then skipped the overflowing tiles)
+__global__ void overflow_flag_kernel(const uint32_t* __restrict__ misc, uint32_t capacity, uint32_t* __restrict__ flag) {
+    if (misc[0] > capacity) atomicOr(flag, 1u);
+    atomicMax(flag + 1, misc[0]);            // largest K seen (lets the host re-size before re-capturing)
+}
+int launch_overflow_flag(const TileWS& t, uint32_t capacity, uint32_t* flag, cudaStream_t s) {
+    overflow_flag_kernel<<<1, 1, 0, s>>>(t.misc, capacity, flag);
+    return 1;
+}
+
 int launch_emit(const gg_view& v, const GeomWS& g, const TileWS& t, const int32_t* radii, uint64_t* keys,
                 uint32_t capacity, cudaStream_t s) {
     const int N = v.num_gaussians;

@@ -264,6 +264,21 @@ int gg_forward_render(const gg_view* view, const gg_inputs* in, const void* geom
     return 0;
 }
 
+int gg_forward_overflow_check(const gg_view* view, const void* tile_ws, int64_t instance_capacity, uint32_t* flag2,
+                              int device, void* stream) {
+    if (int rc = check_view(view)) return rc;
+    if (!tile_ws || !flag2) return fail(GG_E_BADARG, "NULL argument");
+    if (instance_capacity < 0 || instance_capacity > 0xfffffff0ll) return fail(GG_E_BADARG, "instance_capacity out of range");
+    GG_CUDA(cudaSetDevice(device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const int gx = (view->image_width + TILE - 1) / TILE, gy = (view->image_height + TILE - 1) / TILE;
+    TileWS t;
+    tile_layout(const_cast<void*>(tile_ws), gx * gy, &t);
+    g_launches += launch_overflow_flag(t, (uint32_t)instance_capacity, flag2, s);
+    GG_AFTER("overflow_flag_kernel");
+    return 0;
+}
+
 int gg_backward(const gg_view* view, const gg_inputs* in, const void* tile_ws, const void* record_ws,
                 int64_t instance_capacity, const void* image_ws, const int32_t* radii, void* accum_ws,
                 const float* dL_dcolor, const float* dL_ddepth, const float* dL_dalpha, float* dL_dmeans3D,

@@ -130,6 +130,7 @@ int launch_tile_scan(int T, const TileWS& t, cudaStream_t s);
 int launch_sh_color(const gg_view& v, const gg_inputs& in, const GeomWS& g, const int32_t* radii, cudaStream_t s);
 int launch_emit(const gg_view& v, const GeomWS& g, const TileWS& t, const int32_t* radii, uint64_t* keys,
                 uint32_t capacity, cudaStream_t s);
+int launch_overflow_flag(const TileWS& t, uint32_t capacity, uint32_t* flag, cudaStream_t s);
 int launch_sort_pack(const gg_view& v, const GeomWS& g, const TileWS& t, uint64_t* keys, const RecordWS& r,
                      uint32_t capacity, uint32_t max_tile_instances, cudaStream_t s);
 int launch_blend_fwd(const gg_view& v, const gg_inputs& in, const TileWS& t, const RecordWS& r, const ImageWS& img,

@@ -164,11 +164,25 @@ class GradBucket:
         if self.world <= 1 or not dist.is_initialized():
             return
         self.adopt()
-        self._reduce_range(0, self.split, 0)
+        self.exchange_immediate()
         if self.split >= self.numel:
             return
         if self.comm_stream is None or not overlap:
             self._reduce_range(self.split, self.numel, 1)
+            return
+        self.exchange_deferred_async()
+
+    def exchange_immediate(self):
+        """Average the immediate (geometry) block on the current stream."""
+        if self.world > 1 and dist.is_initialized():
+            self._reduce_range(0, self.split, 0)
+
+    def exchange_deferred_async(self):
+        """Average the deferred (SH) block on the side stream, ordered after everything already enqueued on the current
+        stream; the next forward's SH -> RGB kernel (and `wait()`) join it.  Inside a CUDA-graph capture this is called
+        at the START of the captured step (it exchanges what the previous replay's backward left in the bucket), so that
+        the fork / join stays inside one graph."""
+        if self.world <= 1 or not dist.is_initialized() or self.split >= self.numel or self.comm_stream is None:
             return
         cur = torch.cuda.current_stream(self.device)
         ready = torch.cuda.Event()

@@ -90,6 +90,29 @@ def _capacity_for(K: int) -> int:
     return int(K * 1.25) + 4096
 
 
+# CUDA-graph capture: nothing may synchronise, so the forward runs entirely from the hint (a previous eager call with
+# the same (device, N, W, H) must have happened) with extra head-room, and gg_forward_overflow_check leaves the verdict
+# in two sticky device words per device: [overflowed?, largest K seen].  `graph_overflow(device)` reads them.
+GRAPH_HEADROOM = 1.5
+_graph_flags = {}
+
+
+def _graph_flag(dev) -> torch.Tensor:
+    di = dev.index if dev.index is not None else torch.cuda.current_device()
+    f = _graph_flags.get(di)
+    if f is None:
+        f = _graph_flags[di] = torch.zeros(2, dtype=torch.int32, device=dev)
+    return f
+
+
+def graph_overflow(device=None):
+    """(overflowed: bool, largest num_rendered seen) of the sync-free forwards replayed on `device` so far (this
+    call synchronises).  After an overflow: run one eager forward (refreshes the capacity hint) and re-capture."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    f = _graph_flag(dev).tolist()
+    return bool(f[0]), int(f[1]) & 0xFFFFFFFF
+
+
 def _pinned_word(device_index: int) -> torch.Tensor:
     cache = getattr(_tls, "words", None)
     if cache is None:
@@ -193,12 +216,17 @@ class _RasterizeGaussians(torch.autograd.Function):
 
                 if N > 0:
                     STATS["forwards"] += 1
+                    capturing = torch.cuda.is_current_stream_capturing()
                     word = _pinned_word(di)
+                    if not capturing:
+                        _graph_flag(dev)         # the sticky overflow words must exist before any capture starts
                     _capi.check(lib.gg_forward_project(C.byref(view), C.byref(inputs), geom_ws.data_ptr(),
-                                                       tile_ws.data_ptr(), radii.data_ptr(), word.data_ptr(), di, sp),
+                                                       tile_ws.data_ptr(), radii.data_ptr(),
+                                                       None if capturing else word.data_ptr(), di, sp),
                                 "gg_forward_project")
-                    k_ready = torch.cuda.Event()
-                    k_ready.record(stream)
+                    if not capturing:
+                        k_ready = torch.cuda.Event()
+                        k_ready.record(stream)
                     gate = COLOR_GATE.get(di)
                     if gate is not None:
                         stream.wait_event(gate)
@@ -206,21 +234,32 @@ class _RasterizeGaussians(torch.autograd.Function):
                                                      radii.data_ptr(), di, sp), "gg_forward_color")
                     hkey = (di, N, W, H)
                     hint = None if s.debug else _hints.get(hkey)
-                    if hint is not None:
+                    if capturing:
+                        if hint is None:
+                            raise RuntimeError("gaussian-garments_b200: CUDA-graph capture needs one eager forward with "
+                                               "the same (N, width, height) first (it sizes the instance workspaces)")
+                        capacity = int(hint[0] * GRAPH_HEADROOM)
+                        key_ws, record_ws = render(capacity, hint[1])
+                        _capi.check(lib.gg_forward_overflow_check(C.byref(view), tile_ws.data_ptr(), capacity,
+                                                                  _graph_flag(dev).data_ptr(), di, sp),
+                                    "gg_forward_overflow_check")
+                        K, max_tile = -1, hint[1]
+                    elif hint is not None:
                         # everything is enqueued before the host looks at K: the GPU never waits for the host
                         STATS["hinted"] += 1
                         capacity = hint[0]
                         key_ws, record_ws = render(capacity, hint[1])
-                    _t0 = time.perf_counter()
-                    k_ready.synchronize()        # scan + 8-byte copy only; later kernels keep running
-                    STATS["k_wait_s"] += time.perf_counter() - _t0
-                    K, max_tile = (int(v) & 0xFFFFFFFF for v in word.tolist())
-                    if hint is None or K > capacity:
-                        if hint is not None:
-                            STATS["overflow_retries"] += 1
-                        capacity = K
-                        key_ws, record_ws = render(capacity, max_tile)
-                    _hints[hkey] = [max(_capacity_for(K), int(0.9 * (hint[0] if hint else 0))), max_tile]
+                    if not capturing:
+                        _t0 = time.perf_counter()
+                        k_ready.synchronize()        # scan + 8-byte copy only; later kernels keep running
+                        STATS["k_wait_s"] += time.perf_counter() - _t0
+                        K, max_tile = (int(v) & 0xFFFFFFFF for v in word.tolist())
+                        if hint is None or K > capacity:
+                            if hint is not None:
+                                STATS["overflow_retries"] += 1
+                            capacity = K
+                            key_ws, record_ws = render(capacity, max_tile)
+                        _hints[hkey] = [max(_capacity_for(K), int(0.9 * (hint[0] if hint else 0))), max_tile]
                 else:
                     key_ws, record_ws = render(0, 0)
         except Exception:

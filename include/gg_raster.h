@@ -109,6 +109,13 @@ int gg_forward_render(const gg_view* view, const gg_inputs* in, const void* geom
                       int64_t max_tile_instances, void* image_ws, const int32_t* radii,
                       float* out_color, float* out_depth, float* out_alpha, int device, void* stream);
 
+/* ---- sync-free operation (CUDA graphs): upstream blocks on a D2H copy of num_rendered in the middle of every
+ * forward; when the instance workspaces are sized from an earlier call instead, this records on the
+ * device whether that was enough: flag2[0] |= 1 if K > instance_capacity (results of that forward are then
+ * incomplete), flag2[1] = max(flag2[1], K).  flag2: two device words the caller keeps across calls.              */
+int gg_forward_overflow_check(const gg_view* view, const void* tile_ws, int64_t instance_capacity, uint32_t* flag2,
+                              int device, void* stream);
+
 /* ---- backward: replaces `_C.rasterize_gaussians_backward`
  * (renderCUDA bwd + computeCov2DCUDA + preprocessCUDA bwd).
  * Upstream gradients dL_dcolor[3,H,W], dL_ddepth[1,H,W], dL_dalpha[1,H,W] (any may be NULL =
