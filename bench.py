@@ -156,7 +156,10 @@ def make_scene(args, dev):
     st = gg.scenes.mesh_bound_state(args.gaussians)
     cams = gg.scenes.ring_cameras(N_CAMS, width=args.width, height=args.height)
     g = torch.Generator().manual_seed(gg.scenes.SEED + 1)
-    gts = [torch.rand(3, args.height, args.width, generator=g) for _ in range(2)]
+    # ground-truth images are 8-bit, as the reference's PNG frames are; float ground truth = u8 / 255 exactly
+    gts_u8 = [torch.randint(0, 256, (3, args.height, args.width), generator=g, dtype=torch.uint8) for _ in range(2)]
+    gts = [u.float() / 255.0 for u in gts_u8]
+    make_scene.gts_u8 = gts_u8
     return gg, st, cams, gts
 
 
@@ -171,7 +174,7 @@ def run_reference(args, rank, world):
     st = gg.scenes.mesh_bound_state(args.gaussians)
     cams = gg.scenes.ring_cameras(N_CAMS, width=args.width, height=args.height)
     g = torch.Generator().manual_seed(gg.scenes.SEED + 1)
-    gt = torch.rand(3, args.height, args.width, generator=g)
+    gt = torch.randint(0, 256, (3, args.height, args.width), generator=g, dtype=torch.uint8).float() / 255.0
     c_oracle.set_num_threads(_host_cores())            # torchrun exports OMP_NUM_THREADS=1: use every usable core
     cores = c_oracle.num_threads()
 
@@ -262,6 +265,7 @@ def main():
     import copy
     from gaussian_garments_b200 import rasterizer as _rast
     slot_gt = [torch.empty(3, H, W, device=dev) for _ in range(2)]
+    slot_u8 = [torch.zeros(3, H, W, dtype=torch.uint8, device=dev) for _ in range(2)]     # e2e: the H2D payload
     slot_cam = [[torch.empty(4, 4, device=dev), torch.empty(4, 4, device=dev), torch.empty(3, device=dev)] for _ in range(2)]
     slot_loss = [torch.zeros(1, device=dev) for _ in range(2)]
     slot_camobj = []
@@ -277,9 +281,12 @@ def main():
         if gt is not None:
             slot_gt[k].copy_(gt, non_blocking=True)
 
-    def slot_body(k):
+    def slot_body(k, from_u8=False):
         """One step on slot k.  Multi-GPU: the deferred (SH) block of the PREVIOUS step is exchanged on the side stream
-        first and joins at this forward's colour kernel; the immediate block is exchanged after the backward."""
+        first and joins at this forward's colour kernel; the immediate block is exchanged after the backward.
+        from_u8 (end-to-end loop): the slot's 8-bit image, just copied from the host, is dequantised first."""
+        if from_u8:
+            torch.mul(slot_u8[k], 1.0 / 255.0, out=slot_gt[k])
         if world > 1:
             bucket.exchange_deferred_async()
         loss = step(0, slot_gt[k], slot_camobj[k], collective=False)
@@ -310,16 +317,17 @@ def main():
             if world > 1:
                 bucket.wait()
                 dist.barrier()
-            graphs = []
-            for k in range(2):
-                _capi.launch_count(reset=True)
-                g_ = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g_):
-                    slot_body(k)
-                launches_per_replay = _capi.launch_count()
-                graphs.append(g_)
+            graphs, graphs_u8 = [], []
+            for from_u8, dst in ((False, graphs), (True, graphs_u8)):
+                for k in range(2):
+                    _capi.launch_count(reset=True)
+                    g_ = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g_):
+                        slot_body(k, from_u8)
+                    launches_per_replay = _capi.launch_count()
+                    dst.append(g_)
             torch.cuda.synchronize()
-            graph_note = "2 graphs (one per input slot), whole step per launch"
+            graph_note = "whole step per launch; one graph per input slot (x2: device-resident float GT / 8-bit GT from the host)"
         except Exception as e:                             # never lose the bench line to a capture problem
             graphs = None
             graph_note = f"capture failed, eager fallback: {type(e).__name__}: {str(e)[:200]}"
@@ -377,10 +385,10 @@ def main():
     value = world * args.steps / (total_ms * 1e-3)
 
     # ---------------- end-to-end through the public API with host buffers: `e2e` ----------------
-    gt_pinned = [g.pin_memory() for g in gts_cpu]
+    gt_pinned = [u.pin_memory() for u in make_scene.gts_u8]        # 8-bit frames, as a dataloader would hold them
     cam_pinned = [(c.world_view_transform.pin_memory(), c.full_proj_transform.pin_memory(), c.camera_center.pin_memory())
                   for c in cams_cpu]
-    h2d = gt_pinned[0].numel() * 4 + (16 + 16 + 3) * 4
+    h2d = gt_pinned[0].numel() * 1 + (16 + 16 + 3) * 4
 
     # The H2D copy of step i+1's inputs (pinned host -> the slot's device buffers) is issued on a copy stream while step
     # i computes (what a pinned-memory DataLoader with non_blocking copies gives the reference); every copy still
@@ -394,7 +402,7 @@ def main():
     def prefetch(i):
         ci = (i * world + rank) % N_CAMS
         with torch.cuda.stream(copy_stream):
-            slot_gt[i % 2].copy_(gt_pinned[i % 2], non_blocking=True)
+            slot_u8[i % 2].copy_(gt_pinned[i % 2], non_blocking=True)
             for dst, src in zip(slot_cam[i % 2], cam_pinned[ci]):
                 dst.copy_(src, non_blocking=True)
             ready[i % 2].record(copy_stream)
@@ -411,12 +419,13 @@ def main():
                     copy_stream.wait_event(done[(i - 1) % 2])      # slot (i+1)%2 is free once step i-1 has finished
                 prefetch(i + 1)
             if graphs is not None:
-                graphs[k].replay()
+                graphs_u8[k].replay()
                 if i == n - 1 and world > 1:
                     bucket.exchange_deferred_async()
                     bucket.wait()
                 loss = slot_loss[k]
             else:
+                torch.mul(slot_u8[k], 1.0 / 255.0, out=slot_gt[k])
                 loss = step(i, slot_gt[k], slot_camobj[k], drain=(i == n - 1))
             loss_host[k:k + 1].copy_(loss.detach().reshape(1), non_blocking=True)   # D2H read of the result
             done[k].record(cur)
@@ -428,6 +437,16 @@ def main():
         assert len(vals) == n and all(math.isfinite(v) for v in vals)
         return vals
 
+    # PCIe in isolation (diagnostic): one 8-bit frame, pinned host -> device
+    hb0, hb1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(copy_stream):
+        slot_u8[0].copy_(gt_pinned[0], non_blocking=True)
+        hb0.record(copy_stream)
+        for _ in range(4):
+            slot_u8[0].copy_(gt_pinned[0], non_blocking=True)
+        hb1.record(copy_stream)
+    torch.cuda.synchronize()
+    h2d_gbs = 4 * gt_pinned[0].numel() / (hb0.elapsed_time(hb1) * 1e-3) / 1e9
     e2e_run(3)
     torch.cuda.synchronize()
     if world > 1:
@@ -547,9 +566,11 @@ def main():
             "forward_stats": dict(_rasterizer_stats()),
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                    "what": "pinned-host GT image + camera matrices copied H2D every step (on a copy stream, overlapping "
-                            "the previous step's compute), public GaussianRasterizer API fwd + fused L1 + bwd, every step's "
-                            "loss copied D2H (async, read one step later); wall clock, max over ranks", "steps": e_steps},
+                    "what": "pinned-host 8-bit GT frame + camera matrices copied H2D every step (copy stream, overlapping the "
+                            "previous step's compute), dequantised on the device, public GaussianRasterizer API fwd + fused "
+                            "L1 + bwd (CUDA-graph replay of that call sequence unless --eager), every step's loss copied D2H "
+                            "(async, read one step later); wall clock, max over ranks",
+                    "steps": e_steps, "h2d_gbs_measured": h2d_gbs},
             "roofline": roofline}
     if collective is not None:
         line["collective"] = collective
