@@ -14,7 +14,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.environ.get("GG_RASTER_LIB") or os.path.join(CSRC, "libgg_raster.so")   # override: dev experiments
-SOURCES = ["project.cu", "binning.cu", "blend_fwd.cu", "blend_bwd.cu", "blend_bwd2.cu", "preprocess_bwd.cu", "mesh_binding.cu", "photometric.cu", "visibility.cu", "allreduce.cu", "c_api.cu"]
+SOURCES = ["project.cu", "binning.cu", "blend_fwd.cu", "blend_fwd2.cu", "blend_bwd.cu", "blend_bwd2.cu", "preprocess_bwd.cu", "mesh_binding.cu", "photometric.cu", "visibility.cu", "allreduce.cu", "c_api.cu"]
 HEADERS = ["common.cuh", "mesh_binding_math.h", os.path.join("..", "..", "include", "gg_raster.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -111,6 +111,7 @@ def load():
         lib.gg_forward_project.argtypes = [P(GGView), P(GGInputs), vp, vp, vp, vp, i32, vp]
         lib.gg_forward_color.argtypes = [P(GGView), P(GGInputs), vp, vp, i32, vp]
         lib.gg_forward_render.argtypes = [P(GGView), P(GGInputs), vp, vp, vp, vp, i64, i64, vp, vp, vp, vp, vp, i32, vp]
+        lib.gg_forward_render_late_color.argtypes = [P(GGView), P(GGInputs), vp, vp, vp, vp, i64, i64, vp, vp, vp, vp, vp, vp, i32, vp]
         lib.gg_forward_overflow_check.argtypes = [P(GGView), vp, i64, vp, i32, vp]
         lib.gg_backward.argtypes = [P(GGView), P(GGInputs), vp, vp, i64, vp, vp, vp] + [vp] * 11 + [i32, vp]
         lib.gg_mark_visible.argtypes = [C.c_int32, vp, vp, vp, vp, i32, vp]
@@ -135,7 +136,7 @@ def load():
         lib.gg_kernel_times.argtypes = [P(C.c_float)]
         for name in ("gg_forward_workspace_bytes", "gg_instance_workspace_bytes", "gg_backward_workspace_bytes",
                      "gg_forward_project", "gg_forward_color", "gg_forward_render", "gg_backward",
-                     "gg_forward_overflow_check", "gg_mark_visible", "gg_debug_read_geom", "gg_debug_read_binning", "gg_kernel_timing", "gg_kernel_times",
+                     "gg_forward_overflow_check", "gg_forward_render_late_color", "gg_mark_visible", "gg_debug_read_geom", "gg_debug_read_binning", "gg_kernel_timing", "gg_kernel_times",
                      "gg_mesh_bind_workspace_bytes", "gg_mesh_bind_forward", "gg_mesh_bind_backward",
                      "gg_mesh_bind_forward_ex", "gg_mesh_bind_backward_ex", "gg_cast_rays_workspace_bytes",
                      "gg_cast_rays_from_point", "gg_nvls_allreduce_f32",
@@ -156,7 +157,7 @@ def check(rc: int, what: str):
 EXPORTED_SYMBOLS = [
     "gg_abi_version", "gg_version", "gg_last_error", "gg_launch_count", "gg_forward_workspace_bytes",
     "gg_instance_workspace_bytes", "gg_backward_workspace_bytes", "gg_forward_project", "gg_forward_color",
-    "gg_forward_render", "gg_forward_overflow_check", "gg_backward", "gg_mark_visible", "gg_debug_read_geom", "gg_debug_read_binning",
+    "gg_forward_render", "gg_forward_render_late_color", "gg_forward_overflow_check", "gg_backward", "gg_mark_visible", "gg_debug_read_geom", "gg_debug_read_binning",
     "gg_kernel_timing",
     "gg_kernel_count", "gg_kernel_name", "gg_kernel_times", "gg_mesh_bind_workspace_bytes", "gg_mesh_bind_forward",
     "gg_mesh_bind_backward", "gg_mesh_bind_forward_ex", "gg_mesh_bind_backward_ex", "gg_cast_rays_workspace_bytes",

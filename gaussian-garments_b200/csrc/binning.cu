@@ -216,8 +216,25 @@ int launch_emit(const gg_view& v, const GeomWS& g, const TileWS& t, const int32_
     return 1;
 }
 
+// late colours: p2[k].rgb = rgb[id(p2[k])] for every packed instance (ids were parked in p2.w by sort_pack)
+__global__ void __launch_bounds__(256)
+color_fill_kernel(const uint32_t* __restrict__ total, uint32_t capacity, const float* __restrict__ rgb, float4* __restrict__ p2) {
+    const uint32_t n = min(*total, capacity);
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const uint32_t id = __float_as_uint(p2[k].w);
+        p2[k] = make_float4(rgb[3 * (size_t)id], rgb[3 * (size_t)id + 1], rgb[3 * (size_t)id + 2], __uint_as_float(id));
+    }
+}
+int launch_color_fill(const gg_view& v, const GeomWS& g, const TileWS& t, const RecordWS& r, uint32_t capacity, cudaStream_t s) {
+    const int gx = (v.image_width + TILE - 1) / TILE, gy = (v.image_height + TILE - 1) / TILE;
+    if (gx * gy == 0 || v.num_gaussians == 0 || capacity == 0) return 0;
+    const uint32_t blocks = min((capacity + 255u) / 256u, 148u * 16u);
+    color_fill_kernel<<<blocks, 256, 0, s>>>(t.offset + gx * gy, capacity, g.rgb, r.p2);
+    return 1;
+}
+
 int launch_sort_pack(const gg_view& v, const GeomWS& g, const TileWS& t, uint64_t* keys, const RecordWS& r,
-                     uint32_t capacity, uint32_t max_tile_instances, cudaStream_t s) {
+                     uint32_t capacity, uint32_t max_tile_instances, bool with_color, cudaStream_t s) {
     const int gx = (v.image_width + TILE - 1) / TILE, gy = (v.image_height + TILE - 1) / TILE;
     const int T = gx * gy;
     if (T == 0 || v.num_gaussians == 0) return 0;
@@ -232,8 +249,8 @@ int launch_sort_pack(const gg_view& v, const GeomWS& g, const TileWS& t, uint64_
     const size_t bytes = (size_t)smem_keys * sizeof(uint64_t);
     if (bytes > 48 * 1024)
         cudaFuncSetAttribute(sort_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    sort_pack_kernel<<<T, SORT_THREADS, bytes, s>>>(t.offset, keys, g.xy, g.conic_o, g.rgb, r.p0, r.p1, r.p2, capacity,
-                                                     gx, smem_keys);
+    sort_pack_kernel<<<T, SORT_THREADS, bytes, s>>>(t.offset, keys, g.xy, g.conic_o, with_color ? g.rgb : nullptr, r.p0, r.p1,
+                                                     r.p2, capacity, gx, smem_keys);
     return 1;
 }
 

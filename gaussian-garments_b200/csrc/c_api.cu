@@ -184,12 +184,16 @@ int gg_forward_project(const gg_view* view, const gg_inputs* in, void* geom_ws, 
     TileWS t;
     geom_layout(geom_ws, view->num_gaussians > 0 ? view->num_gaussians : 1, &g);
     tile_layout(tile_ws, T, &t);
-    // count and fill are adjacent (count block is 256-aligned): one memset covers both
+    // count | fill | misc are adjacent: one memset covers all three
     GG_CUDA(cudaMemsetAsync(t.count, 0, (size_t)((char*)t.offset - (char*)t.count), s));
-    { ScopedKernelTimer kt(K_PROJECT, s); g_launches += launch_project(*view, *in, g, t, radii, s); }
+    if (view->num_gaussians > 0) {
+        ScopedKernelTimer kt(K_PROJECT, s);     // the tile scan runs in project_kernel's last block
+        g_launches += launch_project(*view, *in, g, t, radii, s);
+    } else {
+        ScopedKernelTimer kt(K_SCAN, s);
+        g_launches += launch_tile_scan(T, t, s);
+    }
     GG_AFTER("project_kernel");
-    { ScopedKernelTimer kt(K_SCAN, s); g_launches += launch_tile_scan(T, t, s); }
-    GG_AFTER("tile_scan_kernel");
     if (num_rendered_host) GG_CUDA(cudaMemcpyAsync(num_rendered_host, t.misc, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     return 0;
 }
@@ -209,10 +213,10 @@ int gg_forward_color(const gg_view* view, const gg_inputs* in, void* geom_ws, co
     return 0;
 }
 
-int gg_forward_render(const gg_view* view, const gg_inputs* in, const void* geom_ws, void* tile_ws, void* key_ws,
-                      void* record_ws, int64_t instance_capacity, int64_t max_tile_instances, void* image_ws,
-                      const int32_t* radii, float* out_color, float* out_depth, float* out_alpha, int device,
-                      void* stream) {
+static int forward_render_impl(const gg_view* view, const gg_inputs* in, const void* geom_ws, void* tile_ws, void* key_ws,
+                               void* record_ws, int64_t instance_capacity, int64_t max_tile_instances, void* image_ws,
+                               const int32_t* radii, float* out_color, float* out_depth, float* out_alpha, bool late_color,
+                               void* color_gate_event, int device, void* stream) {
     if (int rc = check_view(view)) return rc;
     if (int rc = check_inputs(view, in)) return rc;
     if (!geom_ws || !tile_ws || !key_ws || !record_ws || !image_ws || !out_color || !out_depth || !out_alpha)
@@ -250,18 +254,53 @@ int gg_forward_render(const gg_view* view, const gg_inputs* in, const void* geom
         if (!strcmp(e, "lazy")) lazy = true;
         else if (!strcmp(e, "tma")) lazy = false;
     }
+    auto colours = [&]() -> int {                  // late-colour mode: SH -> RGB behind the gate, after the sort
+        if (color_gate_event) GG_CUDA(cudaStreamWaitEvent(s, (cudaEvent_t)color_gate_event, 0));
+        { ScopedKernelTimer kt(K_SHCOLOR, s); g_launches += launch_sh_color(*view, *in, g, radii, s); }
+        return after_launch(view, s, "sh_color_kernel");
+    };
     if (lazy) {
+        if (late_color) { if (int rc = colours()) return rc; }     // the fused kernel packs colours itself
         uint64_t* keys2 = (uint64_t*)((char*)key_ws + align_up((size_t)(instance_capacity > 0 ? instance_capacity : 1) * 8));
         ScopedKernelTimer kt(K_BLENDFWD, s);
         g_launches += launch_blend_fwd_lazy(*view, *in, g, t, (uint64_t*)key_ws, keys2, r, img, cap, out_color,
                                             out_depth, out_alpha, s);
     } else {
-        { ScopedKernelTimer kt(K_SORTPACK, s); g_launches += launch_sort_pack(*view, g, t, (uint64_t*)key_ws, r, cap, (uint32_t)(max_tile_instances < 0 ? 0 : max_tile_instances), s); }
+        {
+            ScopedKernelTimer kt(K_SORTPACK, s);
+            g_launches += launch_sort_pack(*view, g, t, (uint64_t*)key_ws, r, cap,
+                                           (uint32_t)(max_tile_instances < 0 ? 0 : max_tile_instances), !late_color, s);
+        }
         GG_AFTER("sort_pack_kernel");
-        { ScopedKernelTimer kt(K_BLENDFWD, s); g_launches += launch_blend_fwd(*view, *in, t, r, img, cap, out_color, out_depth, out_alpha, s); }
+        if (late_color) {
+            if (int rc = colours()) return rc;
+            g_launches += launch_color_fill(*view, g, t, r, cap, s);
+            GG_AFTER("color_fill_kernel");
+        }
+        // "v2" (default): decoupled warps, branch-free body (blend_fwd2.cu); "v1": round 1's kernel, kept for A/B runs
+        static const bool fwd_v1 = env_is("GG_FWD_KERNEL", "v1");
+        ScopedKernelTimer kt(K_BLENDFWD, s);
+        g_launches += fwd_v1 ? launch_blend_fwd(*view, *in, t, r, img, cap, out_color, out_depth, out_alpha, s)
+                             : launch_blend_fwd2(*view, *in, t, r, img, cap, out_color, out_depth, out_alpha, s);
     }
     GG_AFTER("blend_fwd_kernel");
     return 0;
+}
+
+int gg_forward_render(const gg_view* view, const gg_inputs* in, const void* geom_ws, void* tile_ws, void* key_ws,
+                      void* record_ws, int64_t instance_capacity, int64_t max_tile_instances, void* image_ws,
+                      const int32_t* radii, float* out_color, float* out_depth, float* out_alpha, int device,
+                      void* stream) {
+    return forward_render_impl(view, in, geom_ws, tile_ws, key_ws, record_ws, instance_capacity, max_tile_instances,
+                               image_ws, radii, out_color, out_depth, out_alpha, false, nullptr, device, stream);
+}
+
+int gg_forward_render_late_color(const gg_view* view, const gg_inputs* in, void* geom_ws, void* tile_ws, void* key_ws,
+                                 void* record_ws, int64_t instance_capacity, int64_t max_tile_instances, void* image_ws,
+                                 const int32_t* radii, float* out_color, float* out_depth, float* out_alpha,
+                                 void* color_gate_event, int device, void* stream) {
+    return forward_render_impl(view, in, geom_ws, tile_ws, key_ws, record_ws, instance_capacity, max_tile_instances,
+                               image_ws, radii, out_color, out_depth, out_alpha, true, color_gate_event, device, stream);
 }
 
 int gg_forward_overflow_check(const gg_view* view, const void* tile_ws, int64_t instance_capacity, uint32_t* flag2,

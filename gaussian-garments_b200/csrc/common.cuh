@@ -45,17 +45,17 @@ struct TileWS {
     uint32_t* count;   // [T]   instances per tile          (zeroed by stage 1)
     uint32_t* fill;    // [T]   emit cursor                 (zeroed by stage 1)
     uint32_t* offset;  // [T+1] exclusive scan of count     (kept for backward)
-    uint32_t* misc;    // [8]   misc[0] = K (num_rendered), misc[1] = largest per-tile count
+    uint32_t* misc;    // [8]   misc[0] = K (num_rendered), misc[1] = largest per-tile count, misc[3] = block ticket
 };
 inline size_t tile_layout(void* base, int64_t T, TileWS* ws) {
     char* p = (char*)base;
     size_t o = 0;
     auto take = [&](size_t bytes) { char* q = p ? p + o : nullptr; o += align_up(bytes); return q; };
     TileWS w;
-    w.count = (uint32_t*)take((size_t)T * 4);
+    w.count = (uint32_t*)take((size_t)T * 4);       // count | fill | misc are adjacent: stage 1 zeroes them with one memset
     w.fill = (uint32_t*)take((size_t)T * 4);
-    w.offset = (uint32_t*)take((size_t)(T + 1) * 4);
     w.misc = (uint32_t*)take(8 * 4);
+    w.offset = (uint32_t*)take((size_t)(T + 1) * 4);
     if (ws) *ws = w;
     return o;
 }
@@ -125,16 +125,19 @@ inline size_t accum_layout(void* base, int64_t N, AccumWS* ws) {
 // kernel launchers (defined in the .cu files; each returns the number of kernels it launched)
 // ---------------------------------------------------------------------------------------------
 int launch_project(const gg_view& v, const gg_inputs& in, const GeomWS& g, const TileWS& t, int32_t* radii,
-                   cudaStream_t s);
+                   cudaStream_t s);   // includes the tile scan (last block)
 int launch_tile_scan(int T, const TileWS& t, cudaStream_t s);
 int launch_sh_color(const gg_view& v, const gg_inputs& in, const GeomWS& g, const int32_t* radii, cudaStream_t s);
 int launch_emit(const gg_view& v, const GeomWS& g, const TileWS& t, const int32_t* radii, uint64_t* keys,
                 uint32_t capacity, cudaStream_t s);
+int launch_color_fill(const gg_view& v, const GeomWS& g, const TileWS& t, const RecordWS& r, uint32_t capacity, cudaStream_t s);
 int launch_overflow_flag(const TileWS& t, uint32_t capacity, uint32_t* flag, cudaStream_t s);
 int launch_sort_pack(const gg_view& v, const GeomWS& g, const TileWS& t, uint64_t* keys, const RecordWS& r,
-                     uint32_t capacity, uint32_t max_tile_instances, cudaStream_t s);
+                     uint32_t capacity, uint32_t max_tile_instances, bool with_color, cudaStream_t s);
 int launch_blend_fwd(const gg_view& v, const gg_inputs& in, const TileWS& t, const RecordWS& r, const ImageWS& img,
                      uint32_t capacity, float* out_color, float* out_depth, float* out_alpha, cudaStream_t s);
+int launch_blend_fwd2(const gg_view& v, const gg_inputs& in, const TileWS& t, const RecordWS& r, const ImageWS& img,
+                      uint32_t capacity, float* out_color, float* out_depth, float* out_alpha, cudaStream_t s);
 int launch_blend_fwd_lazy(const gg_view& v, const gg_inputs& in, const GeomWS& g, const TileWS& t, uint64_t* keys,
                           uint64_t* keys2, const RecordWS& r, const ImageWS& img, uint32_t capacity, float* out_color,
                           float* out_depth, float* out_alpha, cudaStream_t s);
@@ -235,6 +238,66 @@ __device__ __forceinline__ float rcp_approx(float x) {   // MUFU.RCP
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+
+// ---- the same primitives on explicit 32-bit shared-window addresses (one pinned base register + compile-time
+// offsets: the generic-pointer forms above make ptxas rebuild the window base -- S2R SR_CgaCtaId + LEA -- per use)
+__device__ __forceinline__ void mbar_init_a(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_a(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_a(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_test_a(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ldsu32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts64(uint32_t addr, float x, float y) {
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(x), "f"(y) : "memory");
+}
+__device__ __forceinline__ float2 lds64(uint32_t addr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 
 // Packed records carry the conic pre-scaled into the log2 domain:
 //   A' = -0.5*log2(e)*A,  B' = -log2(e)*B,  C' = -0.5*log2(e)*C   =>   G = 2^(A' dx^2 + B' dx dy + C' dy^2)
@@ -339,7 +402,10 @@ __device__ __forceinline__ void pack_record(uint64_t key, const float2* __restri
     const float depth = __uint_as_float((uint32_t)(key >> 32));
     const float2 m = xy[id];
     const float4 co = conic_o[id];
-    const float r = rgb[3 * (size_t)id], g = rgb[3 * (size_t)id + 1], b = rgb[3 * (size_t)id + 2];
+    // rgb == nullptr: colours are filled in later (color_fill_kernel) -- the SH -> RGB kernel may still be waiting for
+    // the previous step's SH-gradient exchange while the instances are already being sorted (dist.py)
+    float r = 0.f, g = 0.f, b = 0.f;
+    if (rgb) { r = rgb[3 * (size_t)id]; g = rgb[3 * (size_t)id + 1]; b = rgb[3 * (size_t)id + 2]; }
     // warp-overlap mask: bit w set iff some point of warp w's 8x4 pixel-centre box can reach alpha >= 1/255, i.e.
     // min over the box of f(d) = (A dx^2 + 2 B dx dy + C dy^2)/2 is <= tau = ln(255 o).  First the ellipse's bounding
     // box (cheap reject), then the exact box minimum of the convex quadratic (centre inside -> 0, else the best of

@@ -44,12 +44,72 @@ __device__ __forceinline__ void tile_count_aggregated(bool live, int x0, int y0,
     }
 }
 
+// Exclusive scan of the T per-tile counts by ONE CTA of 256 threads, 2048 counters per round (two 16-byte loads /
+// stores per thread, warp-shuffle scan, one shared-memory hop).  Runs in the LAST block of project_kernel to retire
+// (a separate single-CTA kernel cost 12 us of mostly launch + dependent-load latency); counts are read with ld.cg
+// because other blocks produced them with L2 atomics.
+__device__ void tile_scan_in_block(int T, const uint32_t* __restrict__ count, uint32_t* __restrict__ offset,
+                                   uint32_t* __restrict__ misc) {
+    __shared__ uint32_t s_warp[8];
+    __shared__ uint32_t s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    uint32_t vmax = 0;
+    __syncthreads();
+    for (int base = 0; base < T; base += 2048) {
+        const int i0 = base + tid * 8;
+        uint32_t c[8];
+        if (i0 + 8 <= T && ((reinterpret_cast<uintptr_t>(count) & 15u) == 0)) {
+            const uint4 a = __ldcg(reinterpret_cast<const uint4*>(count + i0));
+            const uint4 b = __ldcg(reinterpret_cast<const uint4*>(count + i0 + 4));
+            c[0] = a.x; c[1] = a.y; c[2] = a.z; c[3] = a.w; c[4] = b.x; c[5] = b.y; c[6] = b.z; c[7] = b.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; k++) c[k] = (i0 + k < T) ? __ldcg(count + i0 + k) : 0u;
+        }
+        uint32_t local = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) { local += c[k]; vmax = max(vmax, c[k]); }
+        uint32_t v = local;                                   // inclusive warp scan of the per-thread sums
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t n = __shfl_up_sync(0xffffffffu, v, d);
+            if (lane >= d) v += n;
+        }
+        if (lane == 31) s_warp[wid] = v;
+        __syncthreads();
+        uint32_t wbase = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) wbase += (w < wid) ? s_warp[w] : 0u;
+        uint32_t run = s_carry + wbase + v - local;           // exclusive prefix of this thread's 8 counters
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            if (i0 + k < T) offset[i0 + k] = run;
+            run += c[k];
+        }
+        __syncthreads();
+        if (tid == 255) s_carry = run;                        // total so far
+        __syncthreads();
+    }
+    vmax = __reduce_max_sync(0xffffffffu, vmax);
+    if (lane == 0) s_warp[wid] = vmax;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t mx = 0;
+        for (int w = 0; w < 8; w++) mx = max(mx, s_warp[w]);
+        offset[T] = s_carry;
+        misc[0] = s_carry;                                    // K = num_rendered
+        misc[1] = mx;                                         // largest per-tile instance count (picks the sort variant)
+    }
+}
+
 __global__ void __launch_bounds__(256)
 project_kernel(int N, const float* __restrict__ means3D, const float* __restrict__ scales,
                const float* __restrict__ rotations, const float* __restrict__ cov3D_precomp,
                const float* __restrict__ opacities, const float* __restrict__ viewmatrix,
                const float* __restrict__ projmatrix, int W, int H, int gx, int gy, float tanfovx, float tanfovy,
-               float mod, GeomWS g, uint32_t* __restrict__ tile_count, int32_t* __restrict__ radii) {
+               float mod, GeomWS g, uint32_t* __restrict__ tile_count, int32_t* __restrict__ radii,
+               uint32_t* __restrict__ tile_offset, uint32_t* __restrict__ misc) {
     __shared__ float cam[32];
     if (threadIdx.x < 16) cam[threadIdx.x] = viewmatrix[threadIdx.x];
     else if (threadIdx.x < 32) cam[threadIdx.x] = projmatrix[threadIdx.x - 16];
@@ -134,6 +194,17 @@ project_kernel(int N, const float* __restrict__ means3D, const float* __restrict
     // per-tile instance counts, warp-aggregated: neighbouring Gaussians (6 per mesh face) mostly hit the
     // same tiles, so lanes that target the same counter elect one leader per iteration (match.any)
     tile_count_aggregated(rad_out > 0, x0, y0, x1, y1, gx, tile_count);
+
+    // last block to retire scans the counters (replaces a separate kernel launch)
+    __shared__ bool s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&misc[3], 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        tile_scan_in_block(gx * gy, tile_count, tile_offset, misc);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -289,7 +360,7 @@ int launch_project(const gg_view& v, const gg_inputs& in, const GeomWS& g, const
     project_kernel<<<(N + 255) / 256, 256, 0, s>>>(N, in.means3D, in.scales, in.rotations, in.cov3D_precomp,
                                                    in.opacities, in.viewmatrix, in.projmatrix, v.image_width,
                                                    v.image_height, gx, gy, v.tanfovx, v.tanfovy, v.scale_modifier, g,
-                                                   t.count, radii);
+                                                   t.count, radii, t.offset, t.misc);
     return 1;
 }
 

@@ -203,15 +203,25 @@ class _RasterizeGaussians(torch.autograd.Function):
                 K, max_tile, capacity = 0, 0, 0
                 key_ws = record_ws = None
 
+                late = {"on": False, "gate": None}
+
                 def render(cap, mt):
                     kb, rb = C.c_size_t(), C.c_size_t()
                     _capi.check(lib.gg_instance_workspace_bytes(cap, C.byref(kb), C.byref(rb)),
                                 "gg_instance_workspace_bytes")
                     kw, rw = _ws(kb.value, dev), _ws(rb.value, dev)
-                    _capi.check(lib.gg_forward_render(C.byref(view), C.byref(inputs), geom_ws.data_ptr(),
-                                                      tile_ws.data_ptr(), kw.data_ptr(), rw.data_ptr(), cap, mt,
-                                                      image_ws.data_ptr(), _ptr(radii), color.data_ptr(),
-                                                      depth.data_ptr(), alpha.data_ptr(), di, sp), "gg_forward_render")
+                    if late["on"]:       # colours after the sort, behind the gate (the SH exchange of the previous step)
+                        _capi.check(lib.gg_forward_render_late_color(
+                            C.byref(view), C.byref(inputs), geom_ws.data_ptr(), tile_ws.data_ptr(), kw.data_ptr(),
+                            rw.data_ptr(), cap, mt, image_ws.data_ptr(), _ptr(radii), color.data_ptr(), depth.data_ptr(),
+                            alpha.data_ptr(), None if late["gate"] is None else late["gate"].cuda_event, di, sp),
+                            "gg_forward_render_late_color")
+                        late["gate"] = None          # a retry after an overflow must not wait again (already passed)
+                    else:
+                        _capi.check(lib.gg_forward_render(C.byref(view), C.byref(inputs), geom_ws.data_ptr(),
+                                                          tile_ws.data_ptr(), kw.data_ptr(), rw.data_ptr(), cap, mt,
+                                                          image_ws.data_ptr(), _ptr(radii), color.data_ptr(),
+                                                          depth.data_ptr(), alpha.data_ptr(), di, sp), "gg_forward_render")
                     return kw, rw
 
                 if N > 0:
@@ -227,13 +237,19 @@ class _RasterizeGaussians(torch.autograd.Function):
                     if not capturing:
                         k_ready = torch.cuda.Event()
                         k_ready.record(stream)
-                    gate = COLOR_GATE.get(di)
-                    if gate is not None:
-                        stream.wait_event(gate)
-                    _capi.check(lib.gg_forward_color(C.byref(view), C.byref(inputs), geom_ws.data_ptr(),
-                                                     radii.data_ptr(), di, sp), "gg_forward_color")
                     hkey = (di, N, W, H)
                     hint = None if s.debug else _hints.get(hkey)
+                    gate = COLOR_GATE.get(di)
+                    # A pending SH-gradient exchange (dist.GradBucket) gates only the colour stage.  With a capacity
+                    # hint the colour stage moves BEHIND emission and sorting (late-colour call), so the exchange
+                    # overlaps with projection + emit + sort; without a hint it simply waits here.
+                    late["on"] = gate is not None and hint is not None
+                    late["gate"] = gate if late["on"] else None
+                    if not late["on"]:
+                        if gate is not None:
+                            stream.wait_event(gate)
+                        _capi.check(lib.gg_forward_color(C.byref(view), C.byref(inputs), geom_ws.data_ptr(),
+                                                         radii.data_ptr(), di, sp), "gg_forward_color")
                     if capturing:
                         if hint is None:
                             raise RuntimeError("gaussian-garments_b200: CUDA-graph capture needs one eager forward with "

@@ -1036,3 +1036,31 @@ def test_densification_cycle_on_device_feeds_the_rasterizer():
         outs.append({k: getattr(m, a).detach().clone() for k, a in NAMES.items()} | {"binding": m.binding.clone()})
     for k in outs[0]:
         assert torch.equal(outs[0][k], outs[1][k]), k
+
+
+def test_late_colour_forward_path_equals_default_path():
+    """Multi-GPU overlap path (dist.GradBucket sets rasterizer.COLOR_GATE): the colour stage runs behind emission and
+    sorting and colours are scattered into the packed records afterwards.  Images must be bit-identical to the default
+    order, gradients equal up to atomics reordering -- also through the overflow retry."""
+    from gaussian_garments_b200 import rasterizer
+    dev, st, cam, S = _api_inputs(6000, (320, 256), seed=7)
+    grads = _upstream_grads(256, 320)
+    rasterizer._hints.clear()
+    a = h.run_cuda(S, st, grads)                       # first call: synchronous, default order; leaves a hint
+    gate = torch.cuda.Event()
+    gate.record(torch.cuda.current_stream())
+    rasterizer.COLOR_GATE[0] = gate
+    try:
+        b = h.run_cuda(S, st, grads)                   # hinted + gated -> late-colour call
+        for key in list(rasterizer._hints):
+            rasterizer._hints[key] = [64, 16]          # overflow -> retry, still late colour (gate already passed)
+        n_retry = rasterizer.STATS["overflow_retries"]
+        c = h.run_cuda(S, st, grads)
+        assert rasterizer.STATS["overflow_retries"] == n_retry + 1
+    finally:
+        rasterizer.COLOR_GATE.pop(0, None)
+    for other in (b, c):
+        for k in ("color", "depth", "alpha", "radii"):
+            assert torch.equal(a[k], other[k]), k
+        for k in ("means3D", "shs", "opacities", "scales", "rotations"):
+            assert h.rel_inf(other["grads"][k], a["grads"][k]) < 1e-4, k
