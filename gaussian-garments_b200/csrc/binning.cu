@@ -218,10 +218,12 @@ int launch_emit(const gg_view& v, const GeomWS& g, const TileWS& t, const int32_
 
 // late colours: p2[k].rgb = rgb[id(p2[k])] for every packed instance (ids were parked in p2.w by sort_pack)
 __global__ void __launch_bounds__(256)
-color_fill_kernel(const uint32_t* __restrict__ total, uint32_t capacity, const float* __restrict__ rgb, float4* __restrict__ p2) {
+color_fill_kernel(const uint32_t* __restrict__ total, uint32_t capacity, uint32_t N, const float* __restrict__ rgb,
+                  float4* __restrict__ p2) {
     const uint32_t n = min(*total, capacity);
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         const uint32_t id = __float_as_uint(p2[k].w);
+        if (id >= N) continue;     // a tile that straddles an undersized capacity was never packed (overflow retry follows)
         p2[k] = make_float4(rgb[3 * (size_t)id], rgb[3 * (size_t)id + 1], rgb[3 * (size_t)id + 2], __uint_as_float(id));
     }
 }
@@ -229,7 +231,7 @@ int launch_color_fill(const gg_view& v, const GeomWS& g, const TileWS& t, const 
     const int gx = (v.image_width + TILE - 1) / TILE, gy = (v.image_height + TILE - 1) / TILE;
     if (gx * gy == 0 || v.num_gaussians == 0 || capacity == 0) return 0;
     const uint32_t blocks = min((capacity + 255u) / 256u, 148u * 16u);
-    color_fill_kernel<<<blocks, 256, 0, s>>>(t.offset + gx * gy, capacity, g.rgb, r.p2);
+    color_fill_kernel<<<blocks, 256, 0, s>>>(t.offset + gx * gy, capacity, (uint32_t)v.num_gaussians, g.rgb, r.p2);
     return 1;
 }
 
