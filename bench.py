@@ -137,8 +137,8 @@ class ClockSampler(threading.Thread):
 def algorithmic_bytes(N, K, P, T, M=16):
     """SURVEY.md 8d / DESIGN.md: compulsory bytes per launch of each kernel (this repo's kernel split)."""
     return {
-        "project": (44 + 4) * N + 44 * N + 4 * K + 8 * T,      # inputs + geom records + tile-count atomics + the tile scan
-        "tile_scan": 8 * T,                                    # (fused into project's last block; separate only for N = 0)
+        "project": (44 + 4) * N + 44 * N + 4 * K,              # inputs + geom records written + tile-count atomics
+        "tile_scan": 8 * T,
         "sh_color": (12 + 12 * M) * N + 12 * N,
         "emit": 20 * N + 8 * K,
         "sort_pack": 8 * K + 36 * K + 48 * K,                   # keys in, gathered geom, packed planes out

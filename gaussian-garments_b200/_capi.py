@@ -6,10 +6,13 @@ or a call fails, a RuntimeError is raised."""
 from __future__ import annotations
 
 import ctypes as C
+import hashlib
 import os
 import shutil
 import subprocess
+import tempfile
 import threading
+import warnings
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
@@ -36,16 +39,8 @@ class GGInputs(C.Structure):
                  "bg", "viewmatrix", "projmatrix", "campos")]
 
 
-def _needs_build() -> bool:
-    if not os.path.exists(LIB_PATH):
-        return True
-    t = os.path.getmtime(LIB_PATH)
-    for f in SOURCES + HEADERS:
-        p = os.path.join(CSRC, f)
-        if os.path.exists(p) and os.path.getmtime(p) > t:
-            return True
-    return False
-
+STAMP_PATH = os.path.join(CSRC, ".build_stamp")
+LOCK_PATH = os.path.join(CSRC, ".build.lock")
 
 # project.cu is compiled with -fmad=false: without FMA contraction its IEEE +,-,*,/,sqrt arithmetic is
 # bit-identical to the CPU oracle's (gcc -ffp-contract=off), so every DISCRETE decision taken from the
@@ -53,31 +48,75 @@ def _needs_build() -> bool:
 PER_FILE_FLAGS = {"project.cu": ["-fmad=false"], "visibility.cu": ["-fmad=false"]}   # ray casts: bit-identical to oracle/raycast_oracle.c
 
 
+def _source_digest() -> str:
+    """sha256 over the sources, headers and flags: staleness is decided by CONTENT (mtimes do not survive a copy to
+    another box, and a stale library must never be loaded silently)."""
+    h = hashlib.sha256()
+    h.update(repr((NVCC_FLAGS, sorted(PER_FILE_FLAGS.items()))).encode())
+    for f in SOURCES + HEADERS:
+        p = os.path.join(CSRC, f)
+        h.update(f.encode())
+        if os.path.exists(p):
+            with open(p, "rb") as fh:
+                h.update(fh.read())
+    return h.hexdigest()
+
+
+def _needs_build() -> bool:
+    if not os.path.exists(LIB_PATH) or os.environ.get("GG_RASTER_LIB"):
+        return not os.path.exists(LIB_PATH)
+    try:
+        with open(STAMP_PATH) as fh:
+            return fh.read().strip() != _source_digest()
+    except OSError:
+        return True
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile csrc/*.cu for sm_100a into csrc/libgg_raster.so (in-tree, so it travels to the GPU box)."""
+    """Compile csrc/*.cu for sm_100a into csrc/libgg_raster.so (in-tree, so it travels to the GPU box).
+    Safe under torchrun: an inter-process file lock serialises builders, objects go to a private temp directory and the
+    finished library is moved into place atomically -- a rank can never dlopen a half-written file."""
     if not force and not _needs_build():
         return LIB_PATH
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("gaussian-garments_b200: nvcc not found and libgg_raster.so is missing/stale")
-    common = [f for f in NVCC_FLAGS if f != "-shared"]
-    procs, objs, log = [], [], ""
-    for src in SOURCES:
-        obj = src.replace(".cu", ".o")
-        objs.append(obj)
-        cmd = [nvcc] + common + PER_FILE_FLAGS.get(src, []) + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
-        procs.append((src, subprocess.Popen(cmd, cwd=CSRC, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-    for src, pr in procs:
-        out, _ = pr.communicate()
-        log += out
-        if pr.returncode != 0:
-            raise RuntimeError(f"nvcc failed on {src}:\n{out}")
-    res = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH] + objs,
-                         cwd=CSRC, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc link failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        print(log)
+    import fcntl
+    with open(LOCK_PATH, "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not _needs_build():          # another process built it while we waited
+                return LIB_PATH
+            digest = _source_digest()
+            tmp = tempfile.mkdtemp(prefix=".build_", dir=CSRC)
+            try:
+                common = [f for f in NVCC_FLAGS if f != "-shared"]
+                procs, objs, log = [], [], ""
+                for src in SOURCES:
+                    obj = os.path.join(tmp, src.replace(".cu", ".o"))
+                    objs.append(obj)
+                    cmd = [nvcc] + common + PER_FILE_FLAGS.get(src, []) + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+                    procs.append((src, subprocess.Popen(cmd, cwd=CSRC, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+                for src, pr in procs:
+                    out, _ = pr.communicate()
+                    log += out
+                    if pr.returncode != 0:
+                        raise RuntimeError(f"nvcc failed on {src}:\n{out}")
+                tmp_lib = os.path.join(tmp, "libgg_raster.so")
+                res = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp_lib] + objs,
+                                     cwd=CSRC, capture_output=True, text=True)
+                if res.returncode != 0:
+                    raise RuntimeError("nvcc link failed:\n" + res.stdout + res.stderr)
+                os.replace(tmp_lib, LIB_PATH)             # atomic on the same filesystem
+                with open(STAMP_PATH + ".tmp", "w") as fh:
+                    fh.write(digest)
+                os.replace(STAMP_PATH + ".tmp", STAMP_PATH)
+                if verbose:
+                    print(log)
+            finally:
+                shutil.rmtree(tmp, ignore_errors=True)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB_PATH
 
 
@@ -92,11 +131,17 @@ def load():
         if _needs_build():
             try:
                 build()
-            except Exception as e:  # stale-but-present library is still usable on a box without nvcc
+            except Exception as e:
                 if not os.path.exists(LIB_PATH):
                     raise RuntimeError(
                         "gaussian-garments_b200: CUDA extension libgg_raster.so is missing and could not be "
                         f"built ({e}); there is no CPU fallback") from e
+                # a library exists but does not match the sources and cannot be rebuilt: never load it silently
+                if os.environ.get("GG_ALLOW_STALE_LIB") != "1":
+                    raise RuntimeError(
+                        "gaussian-garments_b200: libgg_raster.so does not match csrc/ (content hash) and rebuilding "
+                        f"failed ({e}); set GG_ALLOW_STALE_LIB=1 to load it anyway") from e
+                warnings.warn(f"gaussian-garments_b200: loading a STALE libgg_raster.so (rebuild failed: {e})")
         lib = C.CDLL(LIB_PATH)
         vp, i32, i64, sz = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
         P = C.POINTER

@@ -249,8 +249,16 @@ int launch_sort_pack(const gg_view& v, const GeomWS& g, const TileWS& t, uint64_
         if (max_tile_instances == 0) smem_keys = SORT_SMEM_KEYS_MAX;
     }
     const size_t bytes = (size_t)smem_keys * sizeof(uint64_t);
-    if (bytes > 48 * 1024)
-        cudaFuncSetAttribute(sort_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (bytes > 48 * 1024) {   // opt in to large dynamic shared memory; a failure surfaces as a launch error right below
+        static size_t opted[64] = {0};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev < 0 || dev >= 64 || opted[dev] < bytes) {
+            if (cudaFuncSetAttribute(sort_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SORT_SMEM_KEYS_MAX * 8) == cudaSuccess &&
+                dev >= 0 && dev < 64)
+                opted[dev] = (size_t)SORT_SMEM_KEYS_MAX * 8;
+        }
+    }
     sort_pack_kernel<<<T, SORT_THREADS, bytes, s>>>(t.offset, keys, g.xy, g.conic_o, with_color ? g.rgb : nullptr, r.p0, r.p1,
                                                      r.p2, capacity, gx, smem_keys);
     return 1;

@@ -277,8 +277,9 @@ static void b2_launch(int T, cudaStream_t s, const TileWS& t, const RecordWS& r,
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-        cudaFuncSetAttribute(blend_bwd2_kernel<MINB, DA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(B2Smem));
-        attr_set[dev] = true;
+        // a failure here leaves attr_set false and surfaces as a launch error (checked by the C ABI right after)
+        attr_set[dev] = cudaFuncSetAttribute(blend_bwd2_kernel<MINB, DA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)sizeof(B2Smem)) == cudaSuccess;
     }
     blend_bwd2_kernel<MINB, DA><<<T, TILE_PIX, sizeof(B2Smem), s>>>(t.offset, r.p0, r.p1, r.p2, v.image_width,
                                                                     v.image_height, gx, bg, img.n_contrib, img.final_T,

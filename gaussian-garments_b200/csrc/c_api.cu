@@ -1,5 +1,6 @@
 // c_api.cu -- extern "C" boundary (include/gg_raster.h).  Argument validation, workspace
-// carving, launch sequencing, error reporting.  No allocation, no global mutable state.
+// carving, launch sequencing, error reporting.  No allocation.  The only process-wide state is diagnostic: the launch
+// counter and the optional per-kernel timing events (off by default); the compute path itself is re-entrant.
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
@@ -20,8 +21,11 @@ const char* const kKernelNames[K_COUNT] = {"project", "tile_scan", "sh_color", "
                                            "mesh_bind_bwd", "photometric_fwd", "photometric_bwd", "cast_rays"};
 std::atomic<int> g_timing{0};
 std::mutex g_timing_mu;
+// per-kernel timing events belong to ONE device (the one that was current when timing was enabled): launches on any
+// other device are simply not timed (recording a foreign device's event is an invalid-resource-handle error)
 cudaEvent_t g_ev[K_COUNT][2];
 bool g_ev_made = false;
+int g_ev_device = -1;
 bool g_ev_used[K_COUNT] = {false};
 
 struct ScopedKernelTimer {
@@ -30,8 +34,11 @@ struct ScopedKernelTimer {
     bool on;
     ScopedKernelTimer(int slot_, cudaStream_t s_) : slot(slot_), s(s_), on(g_timing.load() != 0) {
         if (on) {
+            int dev = -1;
+            cudaGetDevice(&dev);
             std::lock_guard<std::mutex> lk(g_timing_mu);
-            cudaEventRecord(g_ev[slot][0], s);
+            on = g_ev_made && dev == g_ev_device;
+            if (on) cudaEventRecord(g_ev[slot][0], s);
         }
     }
     ~ScopedKernelTimer() {
@@ -121,10 +128,18 @@ int64_t gg_launch_count(int reset) {
 
 int gg_kernel_timing(int enable) {
     std::lock_guard<std::mutex> lk(g_timing_mu);
+    int dev = -1;
+    GG_CUDA(cudaGetDevice(&dev));
+    if (enable && g_ev_made && dev != g_ev_device) {          // timing moves to the caller's current device
+        for (int k = 0; k < K_COUNT; k++)
+            for (int j = 0; j < 2; j++) cudaEventDestroy(g_ev[k][j]);
+        g_ev_made = false;
+    }
     if (enable && !g_ev_made) {
         for (int k = 0; k < K_COUNT; k++)
             for (int j = 0; j < 2; j++) GG_CUDA(cudaEventCreate(&g_ev[k][j]));
         g_ev_made = true;
+        g_ev_device = dev;
     }
     for (int k = 0; k < K_COUNT; k++) g_ev_used[k] = false;
     g_timing.store(enable ? 1 : 0);
@@ -186,14 +201,10 @@ int gg_forward_project(const gg_view* view, const gg_inputs* in, void* geom_ws, 
     tile_layout(tile_ws, T, &t);
     // count | fill | misc are adjacent: one memset covers all three
     GG_CUDA(cudaMemsetAsync(t.count, 0, (size_t)((char*)t.offset - (char*)t.count), s));
-    if (view->num_gaussians > 0) {
-        ScopedKernelTimer kt(K_PROJECT, s);     // the tile scan runs in project_kernel's last block
-        g_launches += launch_project(*view, *in, g, t, radii, s);
-    } else {
-        ScopedKernelTimer kt(K_SCAN, s);
-        g_launches += launch_tile_scan(T, t, s);
-    }
+    { ScopedKernelTimer kt(K_PROJECT, s); g_launches += launch_project(*view, *in, g, t, radii, s); }
     GG_AFTER("project_kernel");
+    { ScopedKernelTimer kt(K_SCAN, s); g_launches += launch_tile_scan(T, t, s); }
+    GG_AFTER("tile_scan_kernel");
     if (num_rendered_host) GG_CUDA(cudaMemcpyAsync(num_rendered_host, t.misc, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     return 0;
 }

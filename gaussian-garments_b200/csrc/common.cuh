@@ -125,7 +125,7 @@ inline size_t accum_layout(void* base, int64_t N, AccumWS* ws) {
 // kernel launchers (defined in the .cu files; each returns the number of kernels it launched)
 // ---------------------------------------------------------------------------------------------
 int launch_project(const gg_view& v, const gg_inputs& in, const GeomWS& g, const TileWS& t, int32_t* radii,
-                   cudaStream_t s);   // includes the tile scan (last block)
+                   cudaStream_t s);
 int launch_tile_scan(int T, const TileWS& t, cudaStream_t s);
 int launch_sh_color(const gg_view& v, const gg_inputs& in, const GeomWS& g, const int32_t* radii, cudaStream_t s);
 int launch_emit(const gg_view& v, const GeomWS& g, const TileWS& t, const int32_t* radii, uint64_t* keys,

@@ -55,7 +55,7 @@ __device__ __forceinline__ void geom_backward(const PBArgs& A, const float* V, c
     const float a = e.a, b = e.b, c = e.c, det = e.det;
     float dLa = 0.f, dLb = 0.f, dLc = 0.f;
     if (det != 0.f) {
-        const float d2 = 1.f / (det * det);
+        const float d2 = 1.f / (det * det + 0.0000001f);      // upstream keeps the denominator finite the same way
         dLa = d2 * (-c * c * gcA + b * c * gcB - b * b * gcC);
         dLc = d2 * (-b * b * gcA + a * b * gcB - a * a * gcC);
         dLb = d2 * (2.f * b * c * gcA - (det + 2.f * b * b) * gcB + 2.f * a * b * gcC);

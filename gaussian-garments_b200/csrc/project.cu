@@ -44,72 +44,12 @@ __device__ __forceinline__ void tile_count_aggregated(bool live, int x0, int y0,
     }
 }
 
-// Exclusive scan of the T per-tile counts by ONE CTA of 256 threads, 2048 counters per round (two 16-byte loads /
-// stores per thread, warp-shuffle scan, one shared-memory hop).  Runs in the LAST block of project_kernel to retire
-// (a separate single-CTA kernel cost 12 us of mostly launch + dependent-load latency); counts are read with ld.cg
-// because other blocks produced them with L2 atomics.
-__device__ void tile_scan_in_block(int T, const uint32_t* __restrict__ count, uint32_t* __restrict__ offset,
-                                   uint32_t* __restrict__ misc) {
-    __shared__ uint32_t s_warp[8];
-    __shared__ uint32_t s_carry;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (tid == 0) s_carry = 0;
-    uint32_t vmax = 0;
-    __syncthreads();
-    for (int base = 0; base < T; base += 2048) {
-        const int i0 = base + tid * 8;
-        uint32_t c[8];
-        if (i0 + 8 <= T && ((reinterpret_cast<uintptr_t>(count) & 15u) == 0)) {
-            const uint4 a = __ldcg(reinterpret_cast<const uint4*>(count + i0));
-            const uint4 b = __ldcg(reinterpret_cast<const uint4*>(count + i0 + 4));
-            c[0] = a.x; c[1] = a.y; c[2] = a.z; c[3] = a.w; c[4] = b.x; c[5] = b.y; c[6] = b.z; c[7] = b.w;
-        } else {
-#pragma unroll
-            for (int k = 0; k < 8; k++) c[k] = (i0 + k < T) ? __ldcg(count + i0 + k) : 0u;
-        }
-        uint32_t local = 0;
-#pragma unroll
-        for (int k = 0; k < 8; k++) { local += c[k]; vmax = max(vmax, c[k]); }
-        uint32_t v = local;                                   // inclusive warp scan of the per-thread sums
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t n = __shfl_up_sync(0xffffffffu, v, d);
-            if (lane >= d) v += n;
-        }
-        if (lane == 31) s_warp[wid] = v;
-        __syncthreads();
-        uint32_t wbase = 0;
-#pragma unroll
-        for (int w = 0; w < 8; w++) wbase += (w < wid) ? s_warp[w] : 0u;
-        uint32_t run = s_carry + wbase + v - local;           // exclusive prefix of this thread's 8 counters
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            if (i0 + k < T) offset[i0 + k] = run;
-            run += c[k];
-        }
-        __syncthreads();
-        if (tid == 255) s_carry = run;                        // total so far
-        __syncthreads();
-    }
-    vmax = __reduce_max_sync(0xffffffffu, vmax);
-    if (lane == 0) s_warp[wid] = vmax;
-    __syncthreads();
-    if (tid == 0) {
-        uint32_t mx = 0;
-        for (int w = 0; w < 8; w++) mx = max(mx, s_warp[w]);
-        offset[T] = s_carry;
-        misc[0] = s_carry;                                    // K = num_rendered
-        misc[1] = mx;                                         // largest per-tile instance count (picks the sort variant)
-    }
-}
-
 __global__ void __launch_bounds__(256)
 project_kernel(int N, const float* __restrict__ means3D, const float* __restrict__ scales,
                const float* __restrict__ rotations, const float* __restrict__ cov3D_precomp,
                const float* __restrict__ opacities, const float* __restrict__ viewmatrix,
                const float* __restrict__ projmatrix, int W, int H, int gx, int gy, float tanfovx, float tanfovy,
-               float mod, GeomWS g, uint32_t* __restrict__ tile_count, int32_t* __restrict__ radii,
-               uint32_t* __restrict__ tile_offset, uint32_t* __restrict__ misc) {
+               float mod, GeomWS g, uint32_t* __restrict__ tile_count, int32_t* __restrict__ radii) {
     __shared__ float cam[32];
     if (threadIdx.x < 16) cam[threadIdx.x] = viewmatrix[threadIdx.x];
     else if (threadIdx.x < 32) cam[threadIdx.x] = projmatrix[threadIdx.x - 16];
@@ -194,67 +134,83 @@ project_kernel(int N, const float* __restrict__ means3D, const float* __restrict
     // per-tile instance counts, warp-aggregated: neighbouring Gaussians (6 per mesh face) mostly hit the
     // same tiles, so lanes that target the same counter elect one leader per iteration (match.any)
     tile_count_aggregated(rad_out > 0, x0, y0, x1, y1, gx, tile_count);
-
-    // last block to retire scans the counters (replaces a separate kernel launch)
-    __shared__ bool s_last;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(&misc[3], 1u) == gridDim.x - 1);
-    __syncthreads();
-    if (s_last) {
-        __threadfence();
-        tile_scan_in_block(gx * gy, tile_count, tile_offset, misc);
-    }
+    // (Scanning the counters in the last block to retire was tried: the __threadfence every block then needs before
+    //  taking its ticket waits for the block's outstanding counter atomics -- 27 % of this kernel's stall samples,
+    //  +9.5 us -- more than the separate, latency-optimised scan kernel below costs.)
 }
 
 // ---------------------------------------------------------------------------------------------
-// One CTA scans all T tile counts (T <= a few 10^4): thread-serial chunks + warp-shuffle scan.
+// One CTA of 1024 threads scans all T tile counts, 8192 per round: every thread owns 8 consecutive counters (two
+// 16-byte loads issued back to back, two 16-byte stores), warp-shuffle scan, one shared-memory hop across the 32
+// warps.  A 1080p image (8160 tiles) is ONE round: the kernel is a single L2 round trip plus ~100 instructions
+// (round 1's version walked its chunk with two scalar, non-unrolled loops: 16 serialized L2 latencies, 9.7 us).
 __global__ void __launch_bounds__(1024) tile_scan_kernel(int T, const uint32_t* __restrict__ count,
                                                          uint32_t* __restrict__ offset, uint32_t* __restrict__ misc) {
-    __shared__ uint32_t warp_tot[32];
-    const int tid = threadIdx.x;
-    const int per = (T + 1023) / 1024;
-    const int beg = min(tid * per, T), end = min(beg + per, T);
-    uint32_t local = 0, lmax = 0;
-    for (int i = beg; i < end; i++) {
-        const uint32_t c = count[i];
-        local += c;
-        lmax = max(lmax, c);
-    }
-    lmax = __reduce_max_sync(0xffffffffu, lmax);
-    __shared__ uint32_t warp_max[32];
-    if ((tid & 31) == 0) warp_max[tid >> 5] = lmax;
-    // inclusive warp scan
-    uint32_t v = local;
-    const int lane = tid & 31, wid = tid >> 5;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        uint32_t n = __shfl_up_sync(0xffffffffu, v, d);
-        if (lane >= d) v += n;
-    }
-    if (lane == 31) warp_tot[wid] = v;
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    uint32_t vmax = 0;
+    const bool vec = ((reinterpret_cast<uintptr_t>(count) | reinterpret_cast<uintptr_t>(offset)) & 15u) == 0;
     __syncthreads();
-    if (wid == 0) {
-        uint32_t w = warp_tot[lane];
+    for (int base = 0; base < T; base += 8192) {
+        const int i0 = base + tid * 8;
+        uint32_t c[8];
+        const bool full = vec && i0 + 8 <= T;
+        if (full) {
+            const uint4 a = *reinterpret_cast<const uint4*>(count + i0);
+            const uint4 b = *reinterpret_cast<const uint4*>(count + i0 + 4);
+            c[0] = a.x; c[1] = a.y; c[2] = a.z; c[3] = a.w; c[4] = b.x; c[5] = b.y; c[6] = b.z; c[7] = b.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; k++) c[k] = (i0 + k < T) ? count[i0 + k] : 0u;
+        }
+        uint32_t local = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) { local += c[k]; vmax = max(vmax, c[k]); }
+        uint32_t v = local;                                   // inclusive warp scan of the per-thread sums
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            uint32_t n = __shfl_up_sync(0xffffffffu, w, d);
-            if (lane >= d) w += n;
+            const uint32_t n = __shfl_up_sync(0xffffffffu, v, d);
+            if (lane >= d) v += n;
         }
-        warp_tot[lane] = w;
+        if (lane == 31) s_warp[wid] = v;
+        __syncthreads();
+        if (wid == 0) {                                       // scan of the 32 warp totals
+            uint32_t w = s_warp[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t n = __shfl_up_sync(0xffffffffu, w, d);
+                if (lane >= d) w += n;
+            }
+            s_warp[lane] = w;
+        }
+        __syncthreads();
+        uint32_t run = s_carry + (wid > 0 ? s_warp[wid - 1] : 0u) + v - local;     // exclusive prefix of this thread's 8
+        uint32_t o[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) { o[k] = run; run += c[k]; }
+        if (full) {
+            *reinterpret_cast<uint4*>(offset + i0) = make_uint4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<uint4*>(offset + i0 + 4) = make_uint4(o[4], o[5], o[6], o[7]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+                if (i0 + k < T) offset[i0 + k] = o[k];
+        }
+        __syncthreads();
+        if (tid == 1023) s_carry = run;                       // running total
+        __syncthreads();
     }
+    vmax = __reduce_max_sync(0xffffffffu, vmax);
+    if (lane == 0) s_warp[wid] = vmax;
     __syncthreads();
-    uint32_t run = v - local + (wid > 0 ? warp_tot[wid - 1] : 0u);   // exclusive prefix of this chunk
-    for (int i = beg; i < end; i++) {
-        offset[i] = run;
-        run += count[i];
-    }
-    if (tid == 1023) {
-        offset[T] = warp_tot[31];
-        misc[0] = warp_tot[31];                     // K = num_rendered
+    if (tid == 0) {
         uint32_t mx = 0;
-        for (int w = 0; w < 32; w++) mx = max(mx, warp_max[w]);
-        misc[1] = mx;                               // largest per-tile instance count (picks the sort variant)
+        for (int w = 0; w < 32; w++) mx = max(mx, s_warp[w]);
+        offset[T] = s_carry;
+        misc[0] = s_carry;                                    // K = num_rendered
+        misc[1] = mx;                                         // largest per-tile instance count (picks the sort variant)
     }
 }
 
@@ -360,7 +316,7 @@ int launch_project(const gg_view& v, const gg_inputs& in, const GeomWS& g, const
     project_kernel<<<(N + 255) / 256, 256, 0, s>>>(N, in.means3D, in.scales, in.rotations, in.cov3D_precomp,
                                                    in.opacities, in.viewmatrix, in.projmatrix, v.image_width,
                                                    v.image_height, gx, gy, v.tanfovx, v.tanfovy, v.scale_modifier, g,
-                                                   t.count, radii, t.offset, t.misc);
+                                                   t.count, radii);
     return 1;
 }
 

@@ -624,7 +624,7 @@ static int backward_impl(const ggo_state* s, int forward_order, const float* dL_
         float b = u0 * T10 + u1 * T11 + u2 * T12;
         float c = v0 * T10 + v1 * T11 + v2 * T12 + BLUR;
         float det = a * c - b * b;
-        float d2 = 1.f / (det * det);
+        float d2 = 1.f / (det * det + 0.0000001f); /* upstream's guard; det >= 0.09 with the 0.3 px^2 blur, so <= 1.3e-5 relative */
         float dLa = 0, dLb = 0, dLc = 0;
         if (det != 0.f) {
             dLa = d2 * (-c * c * gcA + b * c * gcB - b * b * gcC);
