@@ -256,17 +256,30 @@ sh_color16_kernel(int N, int deg, const float* __restrict__ means3D, const float
     cp_async_wait_all();
     __syncthreads();
     if (!live) return;
-    float sh[48];
-#pragma unroll
-    for (int j = 0; j < 12; j++) {
-        const float4 q = rows[threadIdx.x * SH_ROW_U + j];
-        sh[4 * j] = q.x; sh[4 * j + 1] = q.y; sh[4 * j + 2] = q.z; sh[4 * j + 3] = q.w;
-    }
     float dx = means3D[3 * (size_t)i] - campos[0], dy = means3D[3 * (size_t)i + 1] - campos[1],
           dz = means3D[3 * (size_t)i + 2] - campos[2];
     const float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
+    float b[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) b[k] = 0.f;              // coefficients above the active degree contribute nothing
+    sh_basis(deg, dx * inv, dy * inv, dz * inv, b);
+    const int nb = (deg + 1) * (deg + 1);
+    // accumulate straight out of the padded row (the 48 coefficients never sit in registers together: 72 -> ~40 regs)
+    float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 12; j++) {
+        const float4 q = rows[threadIdx.x * SH_ROW_U + j];
+        const float v[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const int f = 4 * j + e;                          // flat index = 3 k + channel (compile-time)
+            if (f / 3 < nb) acc[f % 3] += b[f / 3] * v[e];    // coefficients above the active degree are ignored
+        }
+    }
     float rgb[3];
-    sh_to_rgb(deg, sh, dx * inv, dy * inv, dz * inv, rgb);
+    rgb[0] = fmaxf(acc[0] + 0.5f, 0.f);
+    rgb[1] = fmaxf(acc[1] + 0.5f, 0.f);
+    rgb[2] = fmaxf(acc[2] + 0.5f, 0.f);
     rgb_out[3 * (size_t)i] = rgb[0];
     rgb_out[3 * (size_t)i + 1] = rgb[1];
     rgb_out[3 * (size_t)i + 2] = rgb[2];
