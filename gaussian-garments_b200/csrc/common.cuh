@@ -26,6 +26,9 @@ struct GeomWS {        // per Gaussian, written by project / sh_color, read by e
     float4* conic_o;   // conic (A,B,C) + opacity
     float* rgb;        // [N,3]
     uint2* rect;       // x0 | y0<<16 , x1 | y1<<16   (tile rectangle, exclusive max)
+    float4* ext;       // alpha >= 1/255 footprint: (half extent x, half extent y, tau = ln(255 o) inflated, kind)
+                       // kind 1 = usable, 2 = degenerate conic (no culling information); per Gaussian, so that the
+                       // per-INSTANCE record packing does not redo two logf / two sqrt / three divisions
 };
 inline size_t geom_layout(void* base, int64_t N, GeomWS* ws) {
     char* p = (char*)base;
@@ -37,6 +40,7 @@ inline size_t geom_layout(void* base, int64_t N, GeomWS* ws) {
     w.conic_o = (float4*)take((size_t)N * 16);
     w.rgb = (float*)take((size_t)N * 12);
     w.rect = (uint2*)take((size_t)N * 8);
+    w.ext = (float4*)take((size_t)N * 16);
     if (ws) *ws = w;
     return o;
 }
@@ -396,53 +400,52 @@ __device__ __forceinline__ bool alpha_extent(float opacity, float cov_xx, float 
 // Build the three packed planes of one (tile, Gaussian) instance from its sort key and the projected
 // per-Gaussian records (shared by sort_pack_kernel and the lazy fused forward).
 __device__ __forceinline__ void pack_record(uint64_t key, const float2* __restrict__ xy,
-                                            const float4* __restrict__ conic_o, const float* __restrict__ rgb,
-                                            float tile_x, float tile_y, float4& q0, float4& q1, float4& q2) {
+                                            const float4* __restrict__ conic_o, const float4* __restrict__ ext,
+                                            const float* __restrict__ rgb, float tile_x, float tile_y, float4& q0,
+                                            float4& q1, float4& q2) {
     const uint32_t id = (uint32_t)(key & 0xffffffffu);
     const float depth = __uint_as_float((uint32_t)(key >> 32));
     const float2 m = xy[id];
     const float4 co = conic_o[id];
+    const float4 E = ext[id];
     // rgb == nullptr: colours are filled in later (color_fill_kernel) -- the SH -> RGB kernel may still be waiting for
     // the previous step's SH-gradient exchange while the instances are already being sorted (dist.py)
     float r = 0.f, g = 0.f, b = 0.f;
     if (rgb) { r = rgb[3 * (size_t)id]; g = rgb[3 * (size_t)id + 1]; b = rgb[3 * (size_t)id + 2]; }
     // warp-overlap mask: bit w set iff some point of warp w's 8x4 pixel-centre box can reach alpha >= 1/255, i.e.
     // min over the box of f(d) = (A dx^2 + 2 B dx dy + C dy^2)/2 is <= tau = ln(255 o).  First the ellipse's bounding
-    // box (cheap reject), then the exact box minimum of the convex quadratic (centre inside -> 0, else the best of
-    // the four edge minima).  tau is inflated by 0.1 % + 1e-3 so rounding in the blend's exponent cannot matter.
+    // box (cheap reject; extents and tau come precomputed per Gaussian from project_kernel), then the exact box
+    // minimum of the convex quadratic (centre inside -> 0, else the best of the four edge minima).  tau is inflated by
+    // 0.1 % + 1e-3 so rounding in the blend's exponent cannot matter.
     uint32_t wmask = 0;
-    const float dc = co.x * co.z - co.y * co.y;
-    float ex, ey;
-    if (dc > 0.f && co.x > 0.f && co.z > 0.f) {
-        if (alpha_extent(co.w, co.z / dc, co.x / dc, ex, ey)) {
-            const float tau = logf(255.0f * co.w) * 1.001f + 1e-3f;
-            const float cx = m.x - tile_x, cy = m.y - tile_y;                       // centre in tile-local pixels
-            const float A = co.x, B = co.y, C = co.z, iA = 1.0f / co.x, iC = 1.0f / co.z;
+    if (E.w == 1.f) {
+        const float ex = E.x, ey = E.y, tau = E.z;
+        const float cx = m.x - tile_x, cy = m.y - tile_y;                       // centre in tile-local pixels
+        const float A = co.x, B = co.y, C = co.z, iA = 1.0f / co.x, iC = 1.0f / co.z;
 #pragma unroll
-            for (int w = 0; w < 8; w++) {
-                const float X0 = (float)((w & 1) * 8), X1 = X0 + 7.f, Y0 = (float)((w >> 1) * 4), Y1 = Y0 + 3.f;
-                if (cx + ex < X0 || cx - ex > X1 || cy + ey < Y0 || cy - ey > Y1) continue;      // bounding-box reject
-                bool hit = (cx >= X0 && cx <= X1 && cy >= Y0 && cy <= Y1);
-                if (!hit) {
-                    float fmin_ = 3.0e38f;
+        for (int w = 0; w < 8; w++) {
+            const float X0 = (float)((w & 1) * 8), X1 = X0 + 7.f, Y0 = (float)((w >> 1) * 4), Y1 = Y0 + 3.f;
+            if (cx + ex < X0 || cx - ex > X1 || cy + ey < Y0 || cy - ey > Y1) continue;      // bounding-box reject
+            bool hit = (cx >= X0 && cx <= X1 && cy >= Y0 && cy <= Y1);
+            if (!hit) {
+                float fmin_ = 3.0e38f;
 #pragma unroll
-                    for (int e = 0; e < 2; e++) {                                   // vertical edges x = X0 / X1
-                        const float u = (e ? X1 : X0) - cx;
-                        const float v = fminf(fmaxf(cy - B * u * iC, Y0), Y1) - cy;
-                        fmin_ = fminf(fmin_, 0.5f * (A * u * u + C * v * v) + B * u * v);
-                    }
-#pragma unroll
-                    for (int e = 0; e < 2; e++) {                                   // horizontal edges y = Y0 / Y1
-                        const float v = (e ? Y1 : Y0) - cy;
-                        const float u = fminf(fmaxf(cx - B * v * iA, X0), X1) - cx;
-                        fmin_ = fminf(fmin_, 0.5f * (A * u * u + C * v * v) + B * u * v);
-                    }
-                    hit = fmin_ <= tau;
+                for (int e = 0; e < 2; e++) {                                   // vertical edges x = X0 / X1
+                    const float u = (e ? X1 : X0) - cx;
+                    const float v = fminf(fmaxf(cy - B * u * iC, Y0), Y1) - cy;
+                    fmin_ = fminf(fmin_, 0.5f * (A * u * u + C * v * v) + B * u * v);
                 }
-                if (hit) wmask |= 1u << w;
+#pragma unroll
+                for (int e = 0; e < 2; e++) {                                   // horizontal edges y = Y0 / Y1
+                    const float v = (e ? Y1 : Y0) - cy;
+                    const float u = fminf(fmaxf(cx - B * v * iA, X0), X1) - cx;
+                    fmin_ = fminf(fmin_, 0.5f * (A * u * u + C * v * v) + B * u * v);
+                }
+                hit = fmin_ <= tau;
             }
+            if (hit) wmask |= 1u << w;
         }
-    } else {
+    } else if (E.w == 2.f) {
         wmask = 0xffu;   // degenerate conic: no culling information
     }
     q0 = make_float4(m.x, m.y, (-0.5f * LOG2E) * co.x, -LOG2E * co.y);

@@ -65,6 +65,7 @@ project_kernel(int N, const float* __restrict__ means3D, const float* __restrict
     uint2 rect = make_uint2(0u, 0u);
     float2 xy = make_float2(0.f, 0.f);
     float4 con = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 ext = make_float4(0.f, 0.f, 0.f, 0.f);
     float depth = 0.f;
     int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
 
@@ -109,6 +110,9 @@ project_kernel(int N, const float* __restrict__ means3D, const float* __restrict
                 // test, so images and gradients are unchanged while K shrinks (~16 % on the cfg2 scene).
                 float ex, ey;
                 if (alpha_extent(op, e.a, e.c, ex, ey)) {
+                    // footprint record for the per-instance warp-overlap mask (common.cuh: pack_record)
+                    const bool regular = (con.x * con.z - con.y * con.y > 0.f) && con.x > 0.f && con.z > 0.f;
+                    ext = make_float4(ex, ey, logf(255.0f * op) * 1.001f + 1e-3f, regular ? 1.f : 2.f);
                     const int sx0 = (int)fmaxf(ceilf((px - ex - (float)(TILE - 1)) / (float)TILE), 0.f);
                     const int sy0 = (int)fmaxf(ceilf((py - ey - (float)(TILE - 1)) / (float)TILE), 0.f);
                     const int sx1 = (int)fminf(floorf((px + ex) / (float)TILE) + 1.f, (float)gx);
@@ -128,6 +132,7 @@ project_kernel(int N, const float* __restrict__ means3D, const float* __restrict
         g.depth[i] = depth;
         g.conic_o[i] = con;
         g.rect[i] = rect;
+        g.ext[i] = ext;
     } else {
         rad_out = 0;
     }
