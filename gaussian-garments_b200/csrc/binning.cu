@@ -106,6 +106,8 @@ __device__ void bitonic_sort_block(Ptr a, uint32_t n) {
 }
 
 constexpr int SORT_THREADS = 256;
+constexpr uint32_t SORT_SMEM_KEYS = 4096;   // default: 32 KB of keys per CTA (7 CTAs/SM)
+constexpr uint32_t SORT_SMEM_KEYS_MAX = 24576;   // 192 KB dynamic variant for dense scenes; beyond: L2/global
 
 // Shared-memory variant with ~4x fewer CTA barriers: every step whose comparators stay inside an
 // aligned 64-key block (all of k <= 64, and the stride <= 32 tail of every later merge) is done by
@@ -163,69 +165,17 @@ __device__ void bitonic_sort_smem(uint64_t* a, uint32_t n) {
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Per-tile sort used by sort_pack_kernel: 32-key runs sorted in REGISTERS (warp-shuffle bitonic, no shared-memory
-// traffic), then log2(n/32) rank-merge levels: every key finds its position in the partner run by binary search and
-// is written straight to its final slot of the other buffer (ping-pong).  For the typical tile (n ~ 160 keys) that
-// is 15 shuffle steps + 3 levels of ~6 probes per key, against 36 compare-exchange sweeps over a 256-slot padded
-// array for the bitonic network (bitonic_sort_smem, still used by the lazy fused forward): ~2.4x fewer instructions
-// and no bank-conflicting strided 64-bit exchanges.  Keys are unique (Gaussian id in the low word); the +inf padding
-// of the last run is kept in order by the "left run strictly-less, right run less-or-equal" tie rule.
-__device__ __forceinline__ uint64_t shfl_xor_u64(uint64_t v, int m) {
-    const uint32_t lo = __shfl_xor_sync(0xffffffffu, (uint32_t)v, m), hi = __shfl_xor_sync(0xffffffffu, (uint32_t)(v >> 32), m);
-    return ((uint64_t)hi << 32) | lo;
-}
-__device__ uint64_t* rank_merge_sort_smem(uint64_t* A, uint64_t* B, uint32_t n) {
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = SORT_THREADS / 32;
-    const uint32_t np = (n + 31u) & ~31u;
-    for (uint32_t base = warp * 32; base < np; base += nwarps * 32) {
-        uint64_t k = (base + lane < n) ? A[base + lane] : ~0ull;
-#pragma unroll
-        for (uint32_t k2 = 2; k2 <= 32; k2 <<= 1) {
-#pragma unroll
-            for (uint32_t j = k2 >> 1; j > 0; j >>= 1) {
-                const uint64_t o = shfl_xor_u64(k, (int)j);
-                const bool ascending = (lane & k2) == 0 || k2 == 32;          // final merge: whole warp ascending
-                const bool lower = (lane & j) == 0;
-                const bool take_min = lower == ascending;
-                k = take_min ? (o < k ? o : k) : (o > k ? o : k);
-            }
-        }
-        A[base + lane] = k;
-    }
-    __syncthreads();
-    uint64_t* src = A;
-    uint64_t* dst = B;
-    for (uint32_t lg = 5; (1u << lg) < np; lg++) {
-        const uint32_t L = 1u << lg;
-        for (uint32_t i = threadIdx.x; i < np; i += SORT_THREADS) {
-            const uint64_t key = src[i];
-            const uint32_t r = i >> lg, p = i & (L - 1);
-            const uint32_t bs = (r ^ 1u) << lg;                                 // partner run [bs, be)
-            uint32_t lo = bs, hi = min(bs + L, np);
-            if (bs >= np) hi = lo = bs;                                         // no partner: rank 0
-            const bool right = r & 1u;
-            while (lo < hi) {
-                const uint32_t mid = (lo + hi) >> 1;
-                const uint64_t v = src[mid];
-                const bool before = right ? (v <= key) : (v < key);             // v sorts before key
-                if (before) lo = mid + 1; else hi = mid;
-            }
-            dst[((r & ~1u) << lg) + p + (lo - bs)] = key;
-        }
-        __syncthreads();
-        uint64_t* t = src; src = dst; dst = t;
-    }
-    return src;
-}
-
+// (A register-shuffle + rank-merge sort -- 32-key runs sorted with warp shuffles, then log2(n/32) levels in which every
+//  key binary-searches its rank in the partner run -- was measured against this network on cfg2, where the 1 900
+//  non-empty tiles hold ~700 keys each: 0.159 ms vs 0.113 ms.  The searches are dependent shared-memory probes, and the
+//  ping-pong buffer halves the CTAs per SM; the network's independent compare-exchanges hide latency better.)
 __global__ void __launch_bounds__(SORT_THREADS)
 sort_pack_kernel(const uint32_t* __restrict__ tile_offset, uint64_t* __restrict__ keys,
                  const float2* __restrict__ xy, const float4* __restrict__ conic_o, const float4* __restrict__ ext,
                  const float* __restrict__ rgb, float4* __restrict__ p0, float4* __restrict__ p1, float4* __restrict__ p2,
-                 uint32_t capacity, int gx, uint32_t smem_keys) {
-    extern __shared__ __align__(16) uint64_t skeys[];            // two buffers of smem_keys keys (ping-pong)
-    const uint32_t t = blockIdx.x;
+                 uint32_t capacity, int gx, uint32_t smem_keys, const uint32_t* __restrict__ order) {
+    extern __shared__ __align__(16) uint64_t skeys[];
+    const uint32_t t = order[blockIdx.x];                      // heaviest tiles first
     const uint32_t off = tile_offset[t];
     uint32_t n = tile_offset[t + 1] - off;
     if (n == 0) return;
@@ -234,7 +184,8 @@ sort_pack_kernel(const uint32_t* __restrict__ tile_offset, uint64_t* __restrict_
     if (n <= smem_keys) {
         for (uint32_t j = threadIdx.x; j < n; j += SORT_THREADS) skeys[j] = keys[off + j];
         __syncthreads();
-        sorted = (n > 1) ? rank_merge_sort_smem(skeys, skeys + smem_keys, n) : skeys;
+        if (n > 1) bitonic_sort_smem(skeys, n);
+        sorted = skeys;
     } else {
         bitonic_sort_block(keys + off, n);
         sorted = keys + off;
@@ -293,24 +244,27 @@ int launch_sort_pack(const gg_view& v, const GeomWS& g, const TileWS& t, uint64_
     const int gx = (v.image_width + TILE - 1) / TILE, gy = (v.image_height + TILE - 1) / TILE;
     const int T = gx * gy;
     if (T == 0 || v.num_gaussians == 0) return 0;
-    // shared-memory budget from the largest tile (two ping-pong buffers of `smem_keys` keys): 1024 keys (16 KB, the
-    // common case) keeps 13 CTAs/SM, 2048 -> 32 KB, 4096 -> 64 KB (opt-in); a tile beyond the budget sorts in global
-    // memory (bitonic_sort_block).  0 = unknown -> the largest tier.
-    uint32_t smem_keys = 1024;
-    if (max_tile_instances == 0 || max_tile_instances > 2048) smem_keys = 4096;
-    else if (max_tile_instances > 1024) smem_keys = 2048;
-    const size_t bytes = (size_t)smem_keys * 2 * sizeof(uint64_t);
+    // shared-memory budget from the largest tile (0 = unknown -> largest variant): 32 KB keeps 7 CTAs/SM for
+    // ordinary scenes; dense scenes trade occupancy for an in-smem sort of up to 24576 keys per tile
+    uint32_t smem_keys = SORT_SMEM_KEYS;
+    if (max_tile_instances == 0 || max_tile_instances > SORT_SMEM_KEYS) {
+        smem_keys = 8192;
+        while (smem_keys < SORT_SMEM_KEYS_MAX && smem_keys < max_tile_instances) smem_keys += 8192;
+        if (max_tile_instances == 0) smem_keys = SORT_SMEM_KEYS_MAX;
+    }
+    const size_t bytes = (size_t)smem_keys * sizeof(uint64_t);
     if (bytes > 48 * 1024) {   // opt in to large dynamic shared memory; a failure surfaces as a launch error right below
-        static bool opted[64] = {false};
+        static size_t opted[64] = {0};
         int dev = 0;
         cudaGetDevice(&dev);
-        if (dev < 0 || dev >= 64 || !opted[dev]) {
-            const bool ok = cudaFuncSetAttribute(sort_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) == cudaSuccess;
-            if (dev >= 0 && dev < 64) opted[dev] = ok;
+        if (dev < 0 || dev >= 64 || opted[dev] < bytes) {
+            if (cudaFuncSetAttribute(sort_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SORT_SMEM_KEYS_MAX * 8) == cudaSuccess &&
+                dev >= 0 && dev < 64)
+                opted[dev] = (size_t)SORT_SMEM_KEYS_MAX * 8;
         }
     }
     sort_pack_kernel<<<T, SORT_THREADS, bytes, s>>>(t.offset, keys, g.xy, g.conic_o, g.ext, with_color ? g.rgb : nullptr, r.p0, r.p1,
-                                                     r.p2, capacity, gx, smem_keys);
+                                                     r.p2, capacity, gx, smem_keys, t.order);
     return 1;
 }
 

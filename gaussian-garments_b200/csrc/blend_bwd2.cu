@@ -56,7 +56,7 @@ constexpr uint32_t XW_WARP_BYTES = B2_ROUND * B2_PITCH * 8, META_WARP_BYTES = B2
 // Everything it needs besides the panel is re-derived here (once per 16 entries) so that nothing stays live in
 // registers across phase 1.
 template <bool DA>
-__device__ __forceinline__ void b2_flush(int cnt, uint32_t sb, int W, int H, int gx, float4* __restrict__ a0,
+__device__ __forceinline__ void b2_flush(int cnt, uint32_t sb, int tile, int W, int H, int gx, float4* __restrict__ a0,
                                          float4* __restrict__ a1, float2* __restrict__ a2) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int e = lane & (B2_ROUND - 1), h = lane >> 4;
@@ -84,7 +84,6 @@ __device__ __forceinline__ void b2_flush(int cnt, uint32_t sb, int W, int H, int
     const uint32_t mb = sb + O_META + (uint32_t)warp * META_WARP_BYTES + 32u * (uint32_t)e;
     const float4 m0 = lds128(mb), m1 = lds128(mb + 16u);
     // shift to the splat centre: dx = ux - cx, dy = uy - cy
-    const int tile = blockIdx.x;
     const float ox = (float)((tile % gx) * TILE + (warp & 1) * 8) + 3.5f;
     const float oy = (float)((tile / gx) * TILE + (warp >> 1) * 4 + 2 * h) + 0.5f;
     const float ux = m0.x - ox, uy = m0.y - oy;
@@ -126,12 +125,12 @@ blend_bwd2_kernel(const uint32_t* __restrict__ tile_offset, const float4* __rest
                   const float* __restrict__ bg, const uint32_t* __restrict__ n_contrib,
                   const float* __restrict__ final_T, const float* __restrict__ dL_dcolor,
                   const float* __restrict__ dL_ddepth, const float* __restrict__ dL_dalpha, float4* __restrict__ a0,
-                  float4* __restrict__ a1, float2* __restrict__ a2) {
+                  float4* __restrict__ a1, float2* __restrict__ a2, const uint32_t* __restrict__ order) {
     extern __shared__ __align__(128) unsigned char b2_raw[];
     uint32_t sb = smem_u32(b2_raw);
     asm volatile("" : "+r"(sb));          // pin: one register, never rematerialised
 
-    const uint32_t tile = blockIdx.x;
+    const uint32_t tile = order[blockIdx.x];              // launch order: heaviest tiles first (tile_scan_kernel)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int px = (tile % gx) * TILE + (warp & 1) * 8 + (lane & 7);
     const int py = (tile / gx) * TILE + (warp >> 1) * 4 + (lane >> 3);
@@ -254,7 +253,7 @@ blend_bwd2_kernel(const uint32_t* __restrict__ tile_offset, const float4* __rest
                 }
                 if (++fill == B2_ROUND) {
                     __syncwarp();
-                    b2_flush<DA>(B2_ROUND, sb, W, H, gx, a0, a1, a2);
+                    b2_flush<DA>(B2_ROUND, sb, (int)tile, W, H, gx, a0, a1, a2);
                     __syncwarp();
                     fill = 0;
                 }
@@ -265,7 +264,7 @@ blend_bwd2_kernel(const uint32_t* __restrict__ tile_offset, const float4* __rest
     }
     if (fill > 0) {
         __syncwarp();
-        b2_flush<DA>(fill, sb, W, H, gx, a0, a1, a2);
+        b2_flush<DA>(fill, sb, (int)tile, W, H, gx, a0, a1, a2);
     }
 }
 
@@ -283,7 +282,7 @@ static void b2_launch(int T, cudaStream_t s, const TileWS& t, const RecordWS& r,
     }
     blend_bwd2_kernel<MINB, DA><<<T, TILE_PIX, sizeof(B2Smem), s>>>(t.offset, r.p0, r.p1, r.p2, v.image_width,
                                                                     v.image_height, gx, bg, img.n_contrib, img.final_T,
-                                                                    dL_dcolor, dL_ddepth, dL_dalpha, acc.a0, acc.a1, acc.a2);
+                                                                    dL_dcolor, dL_ddepth, dL_dalpha, acc.a0, acc.a1, acc.a2, t.order);
 }
 
 int launch_blend_bwd2(const gg_view& v, const gg_inputs& in, const TileWS& t, const RecordWS& r, const ImageWS& img,

@@ -42,12 +42,13 @@ __global__ void __launch_bounds__(TILE_PIX, 5)
 blend_fwd2_kernel(const uint32_t* __restrict__ tile_offset, const float4* __restrict__ p0,
                   const float4* __restrict__ p1, const float4* __restrict__ p2, uint32_t capacity, int W, int H, int gx,
                   const float* __restrict__ bg, float* __restrict__ out_color, float* __restrict__ out_depth,
-                  float* __restrict__ out_alpha, uint32_t* __restrict__ n_contrib, float* __restrict__ final_T) {
+                  float* __restrict__ out_alpha, uint32_t* __restrict__ n_contrib, float* __restrict__ final_T,
+                  const uint32_t* __restrict__ order) {
     __shared__ __align__(128) F2Smem S;
     uint32_t sb = smem_u32(&S);
     asm volatile("" : "+r"(sb));          // pin: one register, never rematerialised
 
-    const uint32_t tile = blockIdx.x;
+    const uint32_t tile = order[blockIdx.x];              // launch order: heaviest tiles first (tile_scan_kernel)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int px = (tile % gx) * TILE + (warp & 1) * 8 + (lane & 7);
     const int py = (tile / gx) * TILE + (warp >> 1) * 4 + (lane >> 3);
@@ -200,7 +201,7 @@ int launch_blend_fwd2(const gg_view& v, const gg_inputs& in, const TileWS& t, co
     const int T = gx * gy;
     if (T == 0) return 0;
     blend_fwd2_kernel<<<T, TILE_PIX, 0, s>>>(t.offset, r.p0, r.p1, r.p2, capacity, v.image_width, v.image_height, gx,
-                                             in.bg, out_color, out_depth, out_alpha, img.n_contrib, img.final_T);
+                                             in.bg, out_color, out_depth, out_alpha, img.n_contrib, img.final_T, t.order);
     return 1;
 }
 

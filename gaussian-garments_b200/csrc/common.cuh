@@ -49,7 +49,9 @@ struct TileWS {
     uint32_t* count;   // [T]   instances per tile          (zeroed by stage 1)
     uint32_t* fill;    // [T]   emit cursor                 (zeroed by stage 1)
     uint32_t* offset;  // [T+1] exclusive scan of count     (kept for backward)
-    uint32_t* misc;    // [8]   misc[0] = K (num_rendered), misc[1] = largest per-tile count, misc[3] = block ticket
+    uint32_t* misc;    // [8]   misc[0] = K (num_rendered), misc[1] = largest per-tile count
+    uint32_t* order;   // [T]   tile indices, heaviest class first (>= 1024, >= 256, >= 1, empty): the blend / sort grids
+                       //       walk the tiles in this order so that the longest CTAs start first (shorter tail)
 };
 inline size_t tile_layout(void* base, int64_t T, TileWS* ws) {
     char* p = (char*)base;
@@ -60,6 +62,7 @@ inline size_t tile_layout(void* base, int64_t T, TileWS* ws) {
     w.fill = (uint32_t*)take((size_t)T * 4);
     w.misc = (uint32_t*)take(8 * 4);
     w.offset = (uint32_t*)take((size_t)(T + 1) * 4);
+    w.order = (uint32_t*)take((size_t)T * 4);
     if (ws) *ws = w;
     return o;
 }

@@ -280,7 +280,7 @@ int launch_cast_rays(int V, int F, int N, const float* verts, const int32_t* fac
         vis_vertex_kernel<<<(V + 255) / 256, 256, 0, s>>>(V, verts, origin, look_at, w.proj, w.misc); n++;
         vis_bin_kernel<false><<<(F + 255) / 256, 256, 0, s>>>(F, faces, w.proj, w.misc, w.count, w.offset, w.fill, w.list, (uint32_t)capacity); n++;
         TileWS t;
-        t.count = w.count; t.fill = w.fill; t.offset = w.offset; t.misc = w.misc;     // misc[0] = total, misc[1] = largest cell
+        t.count = w.count; t.fill = w.fill; t.offset = w.offset; t.misc = w.misc; t.order = nullptr;     // misc[0] = total, misc[1] = largest cell
         n += launch_tile_scan(VIS_CELLS, t, s);
         vis_bin_kernel<true><<<(F + 255) / 256, 256, 0, s>>>(F, faces, w.proj, w.misc, w.count, w.offset, w.fill, w.list, (uint32_t)capacity); n++;
         vis_ray_kernel<<<(N + 255) / 256, 256, 0, s>>>(N, targets, origin, look_at, verts, faces, w.misc, w.offset, w.list,
