@@ -50,7 +50,7 @@ struct TileWS {
     uint32_t* fill;    // [T]   emit cursor                 (zeroed by stage 1)
     uint32_t* offset;  // [T+1] exclusive scan of count     (kept for backward)
     uint32_t* misc;    // [8]   misc[0] = K (num_rendered), misc[1] = largest per-tile count
-    uint32_t* order;   // [T]   tile indices, heaviest class first (>= 1024, >= 256, >= 1, empty): the blend / sort grids
+    uint32_t* order;   // [T]   tile indices, heaviest load class first (64 classes of 32 instances): the blend / sort grids
                        //       walk the tiles in this order so that the longest CTAs start first (shorter tail)
 };
 inline size_t tile_layout(void* base, int64_t T, TileWS* ws) {
