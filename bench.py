@@ -284,12 +284,10 @@ def main():
     def slot_body(k, from_u8=False):
         """One step on slot k.  Multi-GPU: the deferred (SH) block of the PREVIOUS step is exchanged on the side stream
         first and joins at this forward's colour kernel; the immediate block is exchanged after the backward.
-        from_u8 (end-to-end loop): the slot's 8-bit image, just copied from the host, is dequantised first."""
-        if from_u8:
-            torch.mul(slot_u8[k], 1.0 / 255.0, out=slot_gt[k])
+        from_u8 (end-to-end loop): the loss reads the slot's 8-bit image, just copied from the host, directly."""
         if world > 1:
             bucket.exchange_deferred_async()
-        loss = step(0, slot_gt[k], slot_camobj[k], collective=False)
+        loss = step(0, slot_u8[k] if from_u8 else slot_gt[k], slot_camobj[k], collective=False)
         if world > 1:
             bucket.adopt()
             bucket.exchange_immediate()
@@ -425,8 +423,7 @@ def main():
                     bucket.wait()
                 loss = slot_loss[k]
             else:
-                torch.mul(slot_u8[k], 1.0 / 255.0, out=slot_gt[k])
-                loss = step(i, slot_gt[k], slot_camobj[k], drain=(i == n - 1))
+                loss = step(i, slot_u8[k], slot_camobj[k], drain=(i == n - 1))
             loss_host[k:k + 1].copy_(loss.detach().reshape(1), non_blocking=True)   # D2H read of the result
             done[k].record(cur)
             if i >= 1:
@@ -567,7 +564,7 @@ def main():
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "what": "pinned-host 8-bit GT frame + camera matrices copied H2D every step (copy stream, overlapping the "
-                            "previous step's compute), dequantised on the device, public GaussianRasterizer API fwd + fused "
+                            "previous step's compute), dequantised inside the fused L1 kernels, public GaussianRasterizer API fwd + fused "
                             "L1 + bwd (CUDA-graph replay of that call sequence unless --eager), every step's loss copied D2H "
                             "(async, read one step later); wall clock, max over ranks",
                     "steps": e_steps, "h2d_gbs_measured": h2d_gbs},

@@ -172,6 +172,7 @@ def load():
         lib.gg_nvls_allreduce_f32.argtypes = [vp, vp, C.c_int32, C.c_int32, i64, i64, C.c_float, C.c_int32, C.c_int32, i32, vp]
         lib.gg_photometric_workspace_bytes.argtypes = [C.c_int32, C.c_int32, P(sz)]
         lib.gg_photometric_forward.argtypes = [C.c_int32, C.c_int32, vp, vp, vp, vp, C.c_int32, i32, vp]
+        lib.gg_photometric_l1_u8.argtypes = [C.c_int32, C.c_int32, vp, vp, vp, vp, C.c_float, vp, vp, i32, vp]
         lib.gg_photometric_reduce.argtypes = [C.c_int32, C.c_int32, vp, C.c_float, vp, i32, vp]
         lib.gg_photometric_backward.argtypes = [C.c_int32, C.c_int32, vp, vp, vp, vp, C.c_float, C.c_float, vp, vp, i32, vp]
         lib.gg_kernel_timing.argtypes = [i32]
@@ -185,7 +186,7 @@ def load():
                      "gg_mesh_bind_workspace_bytes", "gg_mesh_bind_forward", "gg_mesh_bind_backward",
                      "gg_mesh_bind_forward_ex", "gg_mesh_bind_backward_ex", "gg_cast_rays_workspace_bytes",
                      "gg_cast_rays_from_point", "gg_nvls_allreduce_f32",
-                     "gg_photometric_workspace_bytes", "gg_photometric_forward", "gg_photometric_backward", "gg_photometric_reduce"):
+                     "gg_photometric_workspace_bytes", "gg_photometric_forward", "gg_photometric_backward", "gg_photometric_reduce", "gg_photometric_l1_u8"):
             getattr(lib, name).restype = C.c_int
         if lib.gg_abi_version() != 1:
             raise RuntimeError("gaussian-garments_b200: libgg_raster.so ABI mismatch")
@@ -207,7 +208,7 @@ EXPORTED_SYMBOLS = [
     "gg_kernel_count", "gg_kernel_name", "gg_kernel_times", "gg_mesh_bind_workspace_bytes", "gg_mesh_bind_forward",
     "gg_mesh_bind_backward", "gg_mesh_bind_forward_ex", "gg_mesh_bind_backward_ex", "gg_cast_rays_workspace_bytes",
     "gg_cast_rays_from_point", "gg_nvls_allreduce_f32", "gg_photometric_workspace_bytes", "gg_photometric_forward", "gg_photometric_backward",
-    "gg_photometric_reduce",
+    "gg_photometric_reduce", "gg_photometric_l1_u8",
 ]
 
 

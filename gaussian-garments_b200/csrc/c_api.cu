@@ -606,6 +606,30 @@ int gg_photometric_forward(int32_t width, int32_t height, const float* image, co
     return 0;
 }
 
+// L1-only loss (lambda_dssim = 0) against an 8-bit ground truth [3,H,W], value / 255 (frames as stored / shipped over PCIe).
+// dL_dimage == NULL: forward (accumulates into map_ws like gg_photometric_forward with with_ssim = 0);
+// dL_dimage != NULL: backward (like gg_photometric_backward with coeff_ssim = 0).
+int gg_photometric_l1_u8(int32_t width, int32_t height, const float* image, const uint8_t* gt_u8, const float* mask,
+                         void* map_ws, float coeff_l1, const float* upstream_scalar, float* dL_dimage, int device,
+                         void* stream) {
+    if (width <= 0 || height <= 0 || !image || !gt_u8 || !map_ws) return fail(GG_E_BADARG, "bad size or NULL argument");
+    const size_t plane = (size_t)width * height;
+    if (plane % 4 != 0 || !aligned16(image) || (mask && !aligned16(mask)) || (dL_dimage && !aligned16(dL_dimage)) ||
+        (reinterpret_cast<uintptr_t>(gt_u8) & 3u))
+        return fail(GG_E_ALIGN, "gg_photometric_l1_u8 needs W*H % 4 == 0 and 16-byte aligned float tensors");
+    GG_CUDA(cudaSetDevice(device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const gg_view* view = nullptr;
+    if (!dL_dimage) GG_CUDA(cudaMemsetAsync(map_ws, 0, 1024, s));
+    {
+        ScopedKernelTimer kt(dL_dimage ? K_LOSSBWD : K_LOSSFWD, s);
+        g_launches += launch_photometric_l1_u8(width, height, image, gt_u8, mask, (double*)map_ws, coeff_l1, upstream_scalar,
+                                               dL_dimage, s);
+    }
+    GG_AFTER("photometric_l1_u8");
+    return 0;
+}
+
 int gg_photometric_reduce(int32_t width, int32_t height, const void* map_ws, float lambda_dssim, float* out3, int device,
                           void* stream) {
     if (width <= 0 || height <= 0 || !map_ws || !out3) return fail(GG_E_BADARG, "bad size or NULL argument");

@@ -161,6 +161,8 @@ int launch_preprocess_bwd(const gg_view& v, const gg_inputs& in, const int32_t* 
 int launch_mark_visible(int N, const float* means3D, const float* viewmatrix, uint8_t* visible, cudaStream_t s);
 int launch_photometric_fwd(int W, int H, const float* img, const float* gt, const float* mask, float* m1, float* m2,
                            float* m3, double* sums, cudaStream_t s);
+int launch_photometric_l1_u8(int W, int H, const float* img, const uint8_t* gt8, const float* mask, double* sums,
+                             float c_l1, const float* g_scalar, float* g_img, cudaStream_t s);
 int launch_photometric_finalize(const double* sums, double inv_n, float lambda_dssim, float* out3, cudaStream_t s);
 int launch_photometric_bwd(int W, int H, const float* img, const float* gt, const float* mask, const float* m1,
                            const float* m2, const float* m3, float c_l1, float c_ss, const float* g_scalar, float* g_img,

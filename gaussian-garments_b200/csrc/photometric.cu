@@ -129,13 +129,25 @@ __device__ __forceinline__ float4 ldg_stream(const float4* p) {        // read-o
     return v;
 }
 constexpr int L1_UNROLL = 4;
+// ground truth either float [3,H,W] or 8-bit [3,H,W] (value / 255: frames as they are stored and shipped over PCIe;
+// dequantised on the fly -- a quarter of the bytes and no separate conversion pass)
+template <bool U8>
+__device__ __forceinline__ float4 ldg_gt(const void* base, size_t i4) {
+    if (U8) {
+        const uchar4 q = __ldg(reinterpret_cast<const uchar4*>(base) + i4);
+        const float k = 1.0f / 255.0f;
+        return make_float4(q.x * k, q.y * k, q.z * k, q.w * k);
+    }
+    return ldg_stream(reinterpret_cast<const float4*>(base) + i4);
+}
 // grid (blocks, 3 channels)
+template <bool U8>
 __global__ void __launch_bounds__(256)
-photometric_l1_fwd_vec_kernel(size_t plane4, const float4* __restrict__ img, const float4* __restrict__ gt,
+photometric_l1_fwd_vec_kernel(size_t plane4, const float4* __restrict__ img, const void* __restrict__ gt,
                               const float4* __restrict__ mask, double* __restrict__ sums) {
     __shared__ float red[8];
     const float4* I = img + blockIdx.y * plane4;
-    const float4* G = gt + blockIdx.y * plane4;
+    const size_t G0 = blockIdx.y * plane4;
     float acc = 0.f;
     const size_t stride = (size_t)gridDim.x * 256;
     for (size_t base = (size_t)blockIdx.x * 256 + threadIdx.x; base < plane4; base += stride * L1_UNROLL) {
@@ -145,7 +157,7 @@ photometric_l1_fwd_vec_kernel(size_t plane4, const float4* __restrict__ img, con
             const size_t i = base + u * stride;
             const bool ok = i < plane4;
             a[u] = ok ? ldg_stream(I + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-            b[u] = ok ? ldg_stream(G + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            b[u] = ok ? ldg_gt<U8>(gt, G0 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
             m[u] = (ok && mask) ? mask[i] : make_float4(1.f, 1.f, 1.f, 1.f);
         }
 #pragma unroll
@@ -157,13 +169,14 @@ photometric_l1_fwd_vec_kernel(size_t plane4, const float4* __restrict__ img, con
     if (threadIdx.x == 0) atomicAdd(&sums[(blockIdx.x + 7 * blockIdx.y) & (PHOTO_SLOTS - 1)], (double)t);
 }
 
+template <bool U8>
 __global__ void __launch_bounds__(256)
-photometric_l1_bwd_vec_kernel(size_t plane4, const float4* __restrict__ img, const float4* __restrict__ gt,
+photometric_l1_bwd_vec_kernel(size_t plane4, const float4* __restrict__ img, const void* __restrict__ gt,
                               const float4* __restrict__ mask, float c_l1, const float* __restrict__ g_scalar,
                               float4* __restrict__ g_img) {
     if (g_scalar) c_l1 *= g_scalar[0];
     const float4* I = img + blockIdx.y * plane4;
-    const float4* G = gt + blockIdx.y * plane4;
+    const size_t G0 = blockIdx.y * plane4;
     float4* O = g_img + blockIdx.y * plane4;
     const size_t stride = (size_t)gridDim.x * 256;
     auto sg = [&](float x, float y, float mk) {
@@ -177,7 +190,7 @@ photometric_l1_bwd_vec_kernel(size_t plane4, const float4* __restrict__ img, con
             const size_t i = base + u * stride;
             const bool ok = i < plane4;
             a[u] = ok ? ldg_stream(I + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-            b[u] = ok ? ldg_stream(G + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            b[u] = ok ? ldg_gt<U8>(gt, G0 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
             m[u] = (ok && mask) ? mask[i] : make_float4(1.f, 1.f, 1.f, 1.f);
         }
 #pragma unroll
@@ -278,6 +291,18 @@ int launch_photometric_finalize(const double* sums, double inv_n, float lambda_d
     return 1;
 }
 
+// L1-only loss with an 8-bit ground truth (vector kernels only; the caller guarantees plane % 4 == 0 and alignment)
+int launch_photometric_l1_u8(int W, int H, const float* img, const uint8_t* gt8, const float* mask, double* sums,
+                             float c_l1, const float* g_scalar, float* g_img, cudaStream_t s) {
+    const size_t plane = (size_t)W * H;
+    if (g_img == nullptr)
+        photometric_l1_fwd_vec_kernel<true><<<dim3(148 * 2, 3), 256, 0, s>>>(plane / 4, (const float4*)img, gt8, (const float4*)mask, sums);
+    else
+        photometric_l1_bwd_vec_kernel<true><<<dim3(148 * 2, 3), 256, 0, s>>>(plane / 4, (const float4*)img, gt8, (const float4*)mask,
+                                                                             c_l1, g_scalar, (float4*)g_img);
+    return 1;
+}
+
 int launch_photometric_fwd(int W, int H, const float* img, const float* gt, const float* mask, float* m1, float* m2,
                            float* m3, double* sums, cudaStream_t s) {
     if (W <= 0 || H <= 0) return 0;
@@ -285,8 +310,8 @@ int launch_photometric_fwd(int W, int H, const float* img, const float* gt, cons
         const size_t plane = (size_t)W * H;
         const bool vec = (plane % 4 == 0) && !(((uintptr_t)img | (uintptr_t)gt | (uintptr_t)mask) & 15);
         if (vec) {
-            photometric_l1_fwd_vec_kernel<<<dim3(148 * 2, 3), 256, 0, s>>>(plane / 4, (const float4*)img, (const float4*)gt,
-                                                                           (const float4*)mask, sums);
+            photometric_l1_fwd_vec_kernel<false><<<dim3(148 * 2, 3), 256, 0, s>>>(plane / 4, (const float4*)img, gt,
+                                                                                  (const float4*)mask, sums);
         } else {
             photometric_l1_fwd_kernel<<<148 * 8, 256, 0, s>>>(3 * plane, plane, img, gt, mask, sums);
         }
@@ -302,8 +327,8 @@ int launch_photometric_bwd(int W, int H, const float* img, const float* gt, cons
     if (W <= 0 || H <= 0) return 0;
     const size_t plane = (size_t)W * H;
     if (m1 == nullptr && plane % 4 == 0 && !(((uintptr_t)img | (uintptr_t)gt | (uintptr_t)mask | (uintptr_t)g_img) & 15)) {
-        photometric_l1_bwd_vec_kernel<<<dim3(148 * 2, 3), 256, 0, s>>>(plane / 4, (const float4*)img, (const float4*)gt,
-                                                                       (const float4*)mask, c_l1, g_scalar, (float4*)g_img);
+        photometric_l1_bwd_vec_kernel<false><<<dim3(148 * 2, 3), 256, 0, s>>>(plane / 4, (const float4*)img, gt,
+                                                                              (const float4*)mask, c_l1, g_scalar, (float4*)g_img);
         return 1;
     }
     dim3 grid((W + PT - 1) / PT, (H + PT - 1) / PT, 3);

@@ -33,7 +33,11 @@ class _Photometric(torch.autograd.Function):
     @staticmethod
     def forward(ctx, image, gt, mask, lambda_dssim: float):
         lib = _capi.load()
-        img, g = _prep(image, "image"), _prep(gt, "gt")
+        img = _prep(image, "image")
+        u8 = gt.dtype == torch.uint8                       # 8-bit frame: value / 255, dequantised inside the kernels
+        if u8 and not (lambda_dssim == 0.0 and (img.shape[1] * img.shape[2]) % 4 == 0 and gt.is_cuda):
+            gt, u8 = gt.to(img.device).float() / 255.0, False          # SSIM path / odd sizes: plain conversion
+        g = gt.contiguous() if u8 else _prep(gt, "gt")
         if img.dim() != 3 or img.shape[0] != 3 or g.shape != img.shape:
             raise RuntimeError("photometric_loss expects image and gt of shape [3,H,W]")
         m = None if mask is None else _prep(mask, "mask").reshape(-1)
@@ -47,14 +51,18 @@ class _Photometric(torch.autograd.Function):
         ws = torch.empty(wb.value if lambda_dssim != 0.0 else 1024, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             sp = torch.cuda.current_stream(dev).cuda_stream
-            _capi.check(lib.gg_photometric_forward(W, H, img.data_ptr(), g.data_ptr(), None if m is None else m.data_ptr(),
-                                                   ws.data_ptr(), 1 if lambda_dssim != 0.0 else 0, di, sp), "gg_photometric_forward")
+            if u8:
+                _capi.check(lib.gg_photometric_l1_u8(W, H, img.data_ptr(), g.data_ptr(), None if m is None else m.data_ptr(),
+                                                     ws.data_ptr(), 0.0, None, None, di, sp), "gg_photometric_l1_u8")
+            else:
+                _capi.check(lib.gg_photometric_forward(W, H, img.data_ptr(), g.data_ptr(), None if m is None else m.data_ptr(),
+                                                       ws.data_ptr(), 1 if lambda_dssim != 0.0 else 0, di, sp), "gg_photometric_forward")
             out3 = torch.empty(3, dtype=torch.float32, device=dev)
             _capi.check(lib.gg_photometric_reduce(W, H, ws.data_ptr(), float(lambda_dssim), out3.data_ptr(), di, sp),
                         "gg_photometric_reduce")
         total, l1, ssim_v = out3[0], out3[1], out3[2]
         ctx.save_for_backward(img, g, m if m is not None else torch.empty(0, device=dev), ws)
-        ctx.lam, ctx.hw = float(lambda_dssim), (H, W)
+        ctx.lam, ctx.hw, ctx.u8 = float(lambda_dssim), (H, W), u8
         ctx.mark_non_differentiable(l1, ssim_v)
         return total, l1, ssim_v
 
@@ -70,9 +78,14 @@ class _Photometric(torch.autograd.Function):
         out = torch.empty_like(img)
         with torch.cuda.device(dev):
             sp = torch.cuda.current_stream(dev).cuda_stream
-            _capi.check(lib.gg_photometric_backward(W, H, img.data_ptr(), g.data_ptr(), m.data_ptr() if m.numel() else None,
-                                                    ws.data_ptr(), (1.0 - ctx.lam) / n, -ctx.lam / n, gs.data_ptr(),
-                                                    out.data_ptr(), di, sp), "gg_photometric_backward")
+            if ctx.u8:
+                _capi.check(lib.gg_photometric_l1_u8(W, H, img.data_ptr(), g.data_ptr(), m.data_ptr() if m.numel() else None,
+                                                     ws.data_ptr(), (1.0 - ctx.lam) / n, gs.data_ptr(), out.data_ptr(), di, sp),
+                            "gg_photometric_l1_u8")
+            else:
+                _capi.check(lib.gg_photometric_backward(W, H, img.data_ptr(), g.data_ptr(), m.data_ptr() if m.numel() else None,
+                                                        ws.data_ptr(), (1.0 - ctx.lam) / n, -ctx.lam / n, gs.data_ptr(),
+                                                        out.data_ptr(), di, sp), "gg_photometric_backward")
         return out, None, None, None
 
 

@@ -229,6 +229,13 @@ int gg_nvls_allreduce_f32(void* multicast_base, const void* signal_pads_dev, int
 int gg_photometric_workspace_bytes(int32_t width, int32_t height, size_t* map_bytes);
 int gg_photometric_forward(int32_t width, int32_t height, const float* image, const float* gt, const float* mask,
                            void* map_ws, int32_t with_ssim, int device, void* stream);
+/* L1-only loss (lambda_dssim = 0) against an 8-bit ground truth gt_u8[3,H,W] (= value / 255: frames as they are stored
+ * and shipped over PCIe; dequantised on the fly).  dL_dimage == NULL: forward (fills the accumulator slots of map_ws like
+ * gg_photometric_forward(with_ssim = 0)); dL_dimage != NULL: backward (like gg_photometric_backward(coeff_ssim = 0)).
+ * Needs W*H % 4 == 0.                                                                                               */
+int gg_photometric_l1_u8(int32_t width, int32_t height, const float* image, const uint8_t* gt_u8, const float* mask,
+                         void* map_ws, float coeff_l1, const float* upstream_scalar, float* dL_dimage, int device,
+                         void* stream);
 /* folds the accumulator slots gg_photometric_forward left in map_ws into out3 (device float[3]) =
  * (total, l1_loss, ssim) with total = l1_loss (1 - lambda_dssim) + 1 - ssim lambda_dssim
  * (= loss_dict['img'] + loss_dict['ssim'] of s2_registration.py:259-260); nothing visits the host.              */

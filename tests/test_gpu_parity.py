@@ -1064,3 +1064,25 @@ def test_late_colour_forward_path_equals_default_path():
             assert torch.equal(a[k], other[k]), k
         for k in ("means3D", "shs", "opacities", "scales", "rotations"):
             assert h.rel_inf(other["grads"][k], a["grads"][k]) < 1e-4, k
+
+
+def test_photometric_l1_with_8bit_ground_truth_equals_float_path():
+    """The end-to-end loop ships 8-bit frames over PCIe; the fused L1 kernels dequantise them on the fly (value / 255)."""
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(8)
+    u8 = torch.randint(0, 256, (3, 136, 200), generator=g, dtype=torch.uint8).to(dev)
+    img = torch.rand(3, 136, 200, generator=g).to(dev)
+    mask = (torch.rand(1, 136, 200, generator=g) > 0.3).float().to(dev)
+    for m in (None, mask):
+        a = img.clone().requires_grad_(True)
+        b = img.clone().requires_grad_(True)
+        ta, l1a, _ = gg.photometric_loss(a, u8, m, 0.0)
+        tb, l1b, _ = gg.photometric_loss(b, u8.float() / 255.0, m, 0.0)
+        (ta * 1.3).backward()
+        (tb * 1.3).backward()
+        assert abs(float(l1a) - float(l1b)) < 1e-7 and abs(float(ta) - float(tb)) < 1e-6
+        assert torch.equal(a.grad, b.grad)
+    # SSIM path with an 8-bit ground truth falls back to a plain conversion
+    t1 = gg.photometric_loss(img, u8, None, 0.2)[0]
+    t2 = gg.photometric_loss(img, u8.float() / 255.0, None, 0.2)[0]
+    assert abs(float(t1) - float(t2)) < 1e-6
