@@ -161,6 +161,7 @@ def load():
         lib.gg_backward.argtypes = [P(GGView), P(GGInputs), vp, vp, i64, vp, vp, vp] + [vp] * 11 + [i32, vp]
         lib.gg_mark_visible.argtypes = [C.c_int32, vp, vp, vp, vp, i32, vp]
         lib.gg_debug_read_geom.argtypes = [P(GGView), vp, vp, vp, vp, vp, vp, i32, vp]
+        lib.gg_debug_lazy_phase_counters.argtypes = [vp]
         lib.gg_debug_read_binning.argtypes = [P(GGView), vp, vp, i64, vp, vp, i32, vp]
         lib.gg_mesh_bind_workspace_bytes.argtypes = [C.c_int32, P(sz)]
         lib.gg_mesh_bind_forward.argtypes = [C.c_int32] * 3 + [vp] * 10 + [i32, vp]
@@ -182,7 +183,7 @@ def load():
         lib.gg_kernel_times.argtypes = [P(C.c_float)]
         for name in ("gg_forward_workspace_bytes", "gg_instance_workspace_bytes", "gg_backward_workspace_bytes",
                      "gg_forward_project", "gg_forward_color", "gg_forward_render", "gg_backward",
-                     "gg_forward_overflow_check", "gg_forward_render_late_color", "gg_mark_visible", "gg_debug_read_geom", "gg_debug_read_binning", "gg_kernel_timing", "gg_kernel_times",
+                     "gg_forward_overflow_check", "gg_forward_render_late_color", "gg_mark_visible", "gg_debug_read_geom", "gg_debug_read_binning", "gg_debug_lazy_phase_counters", "gg_kernel_timing", "gg_kernel_times",
                      "gg_mesh_bind_workspace_bytes", "gg_mesh_bind_forward", "gg_mesh_bind_backward",
                      "gg_mesh_bind_forward_ex", "gg_mesh_bind_backward_ex", "gg_cast_rays_workspace_bytes",
                      "gg_cast_rays_from_point", "gg_nvls_allreduce_f32",
@@ -204,7 +205,7 @@ EXPORTED_SYMBOLS = [
     "gg_abi_version", "gg_version", "gg_last_error", "gg_launch_count", "gg_forward_workspace_bytes",
     "gg_instance_workspace_bytes", "gg_backward_workspace_bytes", "gg_forward_project", "gg_forward_color",
     "gg_forward_render", "gg_forward_render_late_color", "gg_forward_overflow_check", "gg_backward", "gg_mark_visible", "gg_debug_read_geom", "gg_debug_read_binning",
-    "gg_kernel_timing",
+    "gg_debug_lazy_phase_counters", "gg_kernel_timing",
     "gg_kernel_count", "gg_kernel_name", "gg_kernel_times", "gg_mesh_bind_workspace_bytes", "gg_mesh_bind_forward",
     "gg_mesh_bind_backward", "gg_mesh_bind_forward_ex", "gg_mesh_bind_backward_ex", "gg_cast_rays_workspace_bytes",
     "gg_cast_rays_from_point", "gg_nvls_allreduce_f32", "gg_photometric_workspace_bytes", "gg_photometric_forward", "gg_photometric_backward",

@@ -288,7 +288,8 @@ blend_fwd_lazy_kernel(const uint32_t* __restrict__ tile_offset, const uint64_t* 
                       float4* __restrict__ p0,
                       float4* __restrict__ p1, float4* __restrict__ p2, uint32_t capacity, int W, int H, int gx,
                       const float* __restrict__ bg, float* __restrict__ out_color, float* __restrict__ out_depth,
-                      float* __restrict__ out_alpha, uint32_t* __restrict__ n_contrib, float* __restrict__ final_T) {
+                      float* __restrict__ out_alpha, uint32_t* __restrict__ n_contrib, float* __restrict__ final_T,
+                      unsigned long long* __restrict__ phase /* diagnostics or NULL: [0] ordering cycles, [1] pack+blend cycles */) {
     __shared__ __align__(16) uint64_t skeys[LZ_CAP];
     __shared__ __align__(16) float4 c0[LZ_CHUNK];
     __shared__ __align__(16) float4 c1[LZ_CHUNK];
@@ -316,7 +317,11 @@ blend_fwd_lazy_kernel(const uint32_t* __restrict__ tile_offset, const uint64_t* 
     const uint32_t a0 = smem_u32(&c0[0]), a1 = smem_u32(&c1[0]), a2 = smem_u32(&c2[0]);
 
     // consume a run of keys that is already in final order; returns true when the whole tile is saturated
+    long long t_blend = 0;                                  // thread 0: cycles inside process_run (pack + blend)
+    const long long t_start = phase ? clock64() : 0;
     auto process_run = [&](const uint64_t* run, uint32_t cnt) -> bool {
+        const long long t_in = phase ? clock64() : 0;
+        struct Tick { long long& acc; long long t0; bool on; __device__ ~Tick() { if (on) acc += clock64() - t0; } } tick{t_blend, t_in, phase != nullptr};
         for (uint32_t c = 0; c < cnt; c += LZ_CHUNK) {
             const uint32_t m = min((uint32_t)LZ_CHUNK, cnt - c);
             if (threadIdx.x < m) {
@@ -442,6 +447,11 @@ blend_fwd_lazy_kernel(const uint32_t* __restrict__ tile_offset, const uint64_t* 
         }
     }
 
+    if (phase && threadIdx.x == 0 && n > 0) {               // everything that was not pack + blend is ordering work
+        const long long total = clock64() - t_start;
+        atomicAdd(&phase[0], (unsigned long long)(total - t_blend));
+        atomicAdd(&phase[1], (unsigned long long)t_blend);
+    }
     if (inside) {
         const size_t P = (size_t)W * H, pid = (size_t)py * W + px;
         out_color[pid] = C0 + T * bg[0];
@@ -454,6 +464,10 @@ blend_fwd_lazy_kernel(const uint32_t* __restrict__ tile_offset, const uint64_t* 
     }
 }
 
+// diagnostics: device pointer to two 64-bit counters the lazy fused forward adds its per-tile phase cycles to
+static unsigned long long* g_lazy_phase = nullptr;
+void set_lazy_phase_counters(unsigned long long* p) { g_lazy_phase = p; }
+
 int launch_blend_fwd_lazy(const gg_view& v, const gg_inputs& in, const GeomWS& g, const TileWS& t, uint64_t* keys,
                           uint64_t* keys2, const RecordWS& r, const ImageWS& img, uint32_t capacity, float* out_color,
                           float* out_depth, float* out_alpha, cudaStream_t s) {
@@ -462,7 +476,7 @@ int launch_blend_fwd_lazy(const gg_view& v, const gg_inputs& in, const GeomWS& g
     if (T == 0) return 0;
     blend_fwd_lazy_kernel<<<T, TILE_PIX, 0, s>>>(t.offset, keys, keys2, g.xy, g.conic_o, g.ext, g.rgb, r.p0, r.p1, r.p2,
                                                  capacity, v.image_width, v.image_height, gx, in.bg, out_color,
-                                                 out_depth, out_alpha, img.n_contrib, img.final_T);
+                                                 out_depth, out_alpha, img.n_contrib, img.final_T, g_lazy_phase);
     return 1;
 }
 

@@ -145,6 +145,7 @@ int launch_blend_fwd(const gg_view& v, const gg_inputs& in, const TileWS& t, con
                      uint32_t capacity, float* out_color, float* out_depth, float* out_alpha, cudaStream_t s);
 int launch_blend_fwd2(const gg_view& v, const gg_inputs& in, const TileWS& t, const RecordWS& r, const ImageWS& img,
                       uint32_t capacity, float* out_color, float* out_depth, float* out_alpha, cudaStream_t s);
+void set_lazy_phase_counters(unsigned long long* p);
 int launch_blend_fwd_lazy(const gg_view& v, const gg_inputs& in, const GeomWS& g, const TileWS& t, uint64_t* keys,
                           uint64_t* keys2, const RecordWS& r, const ImageWS& img, uint32_t capacity, float* out_color,
                           float* out_depth, float* out_alpha, cudaStream_t s);

@@ -23,6 +23,7 @@ Design
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import List, Optional, Sequence
 
 import torch
@@ -87,10 +88,12 @@ class GradBucket:
         self._hdl = hdl
         self._mc_ptr = mc
         self._pads_dev = int(hdl.signal_pad_ptrs_dev)
-        pad_words = int(hdl.signal_pad_size) // 4
-        blocks = max(2, min(72, pad_words // self.world))
-        self._blocks = (max(1, blocks // 3), max(1, blocks - blocks // 3))      # (immediate, deferred)
-        self._slot0 = (0, self._blocks[0] * self.world)
+        if int(hdl.signal_pad_size) // 4 < 2 * self.world:
+            raise RuntimeError("signal pad too small")
+        # grid widths of the data kernel (bytes in flight set its bandwidth); one pad slot range per concurrent instance
+        nb = os.environ.get("GG_AR_BLOCKS", "64,128").split(",")
+        self._blocks = (int(nb[0]), int(nb[-1]))
+        self._slot0 = (0, self.world)
         self.flat = flat
         self.impl = "nvls_multimem"
         torch.cuda.synchronize(dev)

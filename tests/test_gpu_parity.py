@@ -1086,3 +1086,66 @@ def test_photometric_l1_with_8bit_ground_truth_equals_float_path():
     t1 = gg.photometric_loss(img, u8, None, 0.2)[0]
     t2 = gg.photometric_loss(img, u8.float() / 255.0, None, 0.2)[0]
     assert abs(float(t1) - float(t2)) < 1e-6
+
+
+# ------------------------------------------------------------------------------------ BASELINE-size cfg4 / cfg5 parity
+def test_cfg4_full_size_mixed_resolution_with_mesh_vertex_gradient():
+    """BASELINE configs[3] at full size: 150k mesh-bound Gaussians (25k faces x 6), SH degree 0 with an [N,1,3] tensor
+    (s2_registration.py:158), one 1280x720 and one 1920x1080 camera of the 32-camera ring, gradients chained to mesh.v
+    ONLY (scene/mesh_gaussian_model.py:366-371) through the fused mesh binding.  Reference: C oracle for the rasterizer
+    (its dL/d{means3D, scales, rotations}) chained through autograd (fp64) over oracle/mesh_chain.py to mesh.v."""
+    from oracle import mesh_chain as mc
+    dev = torch.device("cuda:0")
+    model = gg.scenes.MeshBoundGaussians(250, 50, 6, sh_degree=0, max_sh_degree=0)          # 25 000 faces -> 150 000
+    assert model.binding.shape[0] == 150_000
+    st = model.world_state()
+    ring720, ring1080 = gg.scenes.ring_cameras(32, width=1280, height=720), gg.scenes.ring_cameras(32, width=1920, height=1080)
+    total_ref = torch.zeros_like(model.mesh_v, dtype=torch.float64)
+    total_got = torch.zeros_like(model.mesh_v)
+    for cam in (ring720[6], ring1080[7]):
+        H, W = cam.image_height, cam.image_width
+        S = h.settings_for(cam, st, device=dev)
+        ref = h.run_c_oracle(S, st, None)
+        grads = h.mask_upstream(_upstream_grads(H, W, seed=H, depth_alpha=False), ref["fragile"])
+        rg = ref["ctx"].backward(*grads)
+        # reference chain to mesh.v (fp64 autograd through the golden-pinned restatement of the binding)
+        v64 = model.mesh_v.double().requires_grad_(True)
+        chain = mc.MeshChain(v64, model.mesh_f, model.binding, model._xyz.double(), model._scaling.double(), model._rotation.double())
+        chain.update_face_coor()
+        ((chain.get_xyz * rg["means3D"].double()).sum() + (chain.get_scaling * rg["scales"].double()).sum() +
+         (chain.get_rotation * rg["rotations"].double()).sum()).backward()
+        total_ref += v64.grad
+        # product: fused binding -> rasterizer -> backward to mesh.v
+        m = gg.scenes.MeshBoundGaussians(250, 50, 6, sh_degree=0, max_sh_degree=0).to(dev)
+        m.mesh_v = m.mesh_v.detach().clone().requires_grad_(True)
+        xyz, sc, ro = gg.FusedMeshBinding(m).world()
+        color, radii, _, _ = h.dgr.GaussianRasterizer(raster_settings=S)(
+            means3D=xyz, means2D=torch.zeros_like(xyz), shs=m.get_features, colors_precomp=None, opacities=m.get_opacity,
+            scales=sc, rotations=ro, cov3D_precomp=None)
+        assert int((radii.cpu() != ref["radii"]).sum()) <= 3
+        h.assert_images_close(dict(color=color.detach().cpu(), depth=ref["depth"], alpha=ref["alpha"]), ref)
+        (color * grads[0].to(dev)).sum().backward()
+        total_got += m.mesh_v.grad.cpu()
+        ref["ctx"].close()
+    err = h.rel_inf(total_got, total_ref.float())
+    h._note("cfg4_full", mesh_v_rel_inf=err, verts=int(model.mesh_v.shape[0]))
+    assert err <= h.GRAD_TOL, f"mesh.v gradient over the 720p + 1080p views: rel-inf {err:.3e}"
+
+
+def test_cfg5_half_million_gaussians_at_2160p_parity():
+    """BASELINE configs[4] shape at a size the C oracle finishes in about a minute: 500k stress-cloud Gaussians on one
+    3840x2160 camera (thousands of instances per tile -> the lazy bucketed forward), forward + gradients at 1e-4 / 1e-3."""
+    st = gg.scenes.stress_cloud(500_000)
+    cam = gg.scenes.ring_cameras(160, width=3840, height=2160)[11]
+    S = h.settings_for(cam, st, device=torch.device("cuda:0"))
+    ref = h.run_c_oracle(S, st, None)
+    grads = h.mask_upstream(_upstream_grads(2160, 3840, seed=9), ref["fragile"])
+    got = h.run_cuda(S, st, grads)
+    ref["grads"] = ref["ctx"].backward(*grads)
+    off = ref["ctx"].binning()["tile_off"]
+    assert int((off[1:] - off[:-1]).max()) > 4096
+    assert int((got["radii"] != ref["radii"]).sum()) <= 5
+    h.assert_images_close(got, ref, max_fragile_frac=0.05)
+    h.assert_grads_close(got["grads"], ref["grads"])
+    h._note("cfg5_500k", K_oracle=int(off[-1]), max_tile=int((off[1:] - off[:-1]).max()))
+    ref["ctx"].close()
