@@ -10,11 +10,13 @@
 //         v *= 1/world                                    (the averaging is fused here)
 //         multimem.st.v4.f32 [mc + i], v                  the switch writes the result into every rank's bucket
 // Per GPU ~ bytes/world in + bytes out per phase instead of 2 (world-1)/world x bytes through a ring, and the adds
-// happen in the switch.  Cross-rank ordering uses the symmetric-memory signal pads: a one-warp kernel exchanges one
-// flag with every peer before the data kernel (all ranks' gradients are complete) and one after it (all results have
-// landed); the data kernel's grid is as wide as the links need (bytes in flight, not instruction rate, set the
-// bandwidth: a round trip through the switch is ~2-3 us).  Two instances may be in flight on different streams
-// (geometry block / SH block) -- they use disjoint pad slots.
+// happen in the switch.  Cross-rank ordering uses the symmetric-memory signal pads: every block exchanges one flag
+// with the same block of every peer on entry (all ranks' gradients are complete) and on exit (all results landed).
+// Two instances may be in flight on different streams (geometry block / SH block) -- they use disjoint pad channels.
+// (Measured alternative, 8 x B200: one-warp barrier kernels around a wide -- 64 to 256 block -- data kernel.  The
+//  exchange got SLOWER, 0.218-0.237 ms vs 0.2045 ms for 70.8 MB, and the step 0.82 vs 0.72 ms: the in-switch reduction
+//  saturates at ~350 GB/s algorithmic with ~45 blocks in flight, and a wider grid only takes SM slots from the compute
+//  kernels the deferred block overlaps with.)
 #include "common.cuh"
 
 namespace gg {
@@ -38,15 +40,14 @@ __device__ __forceinline__ uint32_t cas_sys_acquire(uint32_t* a, uint32_t cmp, u
     return old;
 }
 
-// Cross-rank flags live in the signal pads: thread t < world of ONE block (block 0) raises the flag in peer t's pad
-// and waits for peer t's flag in ours.  Flags toggle 0 -> 1 (raise) -> 0 (consume), so the pads are ready for the next
-// call without a reset.
+// One flag per (block, peer): thread t < world raises the flag in peer t's pad and waits for peer t's flag in ours.
+// Flags toggle 0 -> 1 (raise) -> 0 (consume), so the pads are ready for the next call without a reset.
 template <bool RELEASE_ACQUIRE>
 __device__ __forceinline__ void cross_rank_barrier(uint32_t* const* __restrict__ pads, int rank, int world, int slot0) {
     if ((int)threadIdx.x < world) {
         const int peer = threadIdx.x;
-        uint32_t* theirs = pads[peer] + slot0 + rank;
-        uint32_t* mine = pads[rank] + slot0 + peer;
+        uint32_t* theirs = pads[peer] + slot0 + (int)blockIdx.x * world + rank;
+        uint32_t* mine = pads[rank] + slot0 + (int)blockIdx.x * world + peer;
         if (RELEASE_ACQUIRE) {
             while (cas_sys_release(theirs, 0u, 1u) != 0u) {}
             while (cas_sys_acquire(mine, 1u, 0u) != 1u) {}
@@ -56,20 +57,16 @@ __device__ __forceinline__ void cross_rank_barrier(uint32_t* const* __restrict__
         }
     }
 }
-// entry / exit barrier as their own one-warp kernels around the wide data kernel: while a rank waits for late peers
-// only ONE warp spins (a wide grid parked on the barrier would hold ~30 % of the SM's thread slots hostage from the
-// compute kernels that overlap with the exchange)
-template <bool RELEASE_ACQUIRE>
-__global__ void __launch_bounds__(32) nvls_barrier_kernel(uint32_t* const* __restrict__ pads, int rank, int world, int slot0) {
-    if (RELEASE_ACQUIRE) __threadfence_system();
-    cross_rank_barrier<RELEASE_ACQUIRE>(pads, rank, world, slot0);
-}
 
 __global__ void __launch_bounds__(AR_THREADS)
-nvls_reduce_kernel(float* __restrict__ mc, int rank, int world, int64_t n_vec4, float scale) {
+nvls_allreduce_kernel(float* __restrict__ mc, uint32_t* const* __restrict__ pads, int rank, int world, int slot0,
+                      int64_t n_vec4, float scale) {
+    cross_rank_barrier<false>(pads, rank, world, slot0);      // every rank's producer kernels have finished
+    __syncthreads();
     const int64_t per = (n_vec4 + world - 1) / world;
     const int64_t beg = min((int64_t)rank * per, n_vec4), end = min(beg + per, n_vec4);
-    // AR_UNROLL independent 16-byte reductions in flight per thread
+    // AR_UNROLL independent 16-byte reductions in flight per thread: one round trip through the switch is ~2-3 us, so
+    // bytes in flight (blocks x 512 x 16 B x AR_UNROLL) set the bandwidth, not the instruction rate
     const int64_t stride = (int64_t)gridDim.x * AR_THREADS;
     for (int64_t i0 = beg + (int64_t)blockIdx.x * AR_THREADS + threadIdx.x; i0 < end; i0 += stride * AR_UNROLL) {
         float4 v[AR_UNROLL];
@@ -91,16 +88,15 @@ nvls_reduce_kernel(float* __restrict__ mc, int rank, int world, int64_t n_vec4, 
                              : "memory");
         }
     }
-    __threadfence_system();
+    __syncthreads();
+    cross_rank_barrier<true>(pads, rank, world, slot0);       // every rank's slice has landed everywhere
 }
 
 int launch_nvls_allreduce(float* mc, uint32_t* const* pads, int rank, int world, int slot0, int64_t n_vec4, float scale,
                           int blocks, cudaStream_t s) {
     if (n_vec4 <= 0) return 0;
-    nvls_barrier_kernel<false><<<1, 32, 0, s>>>(pads, rank, world, slot0);       // every rank's gradients are complete
-    nvls_reduce_kernel<<<blocks, AR_THREADS, 0, s>>>(mc, rank, world, n_vec4, scale);
-    nvls_barrier_kernel<true><<<1, 32, 0, s>>>(pads, rank, world, slot0);        // every rank's slice landed everywhere
-    return 3;
+    nvls_allreduce_kernel<<<blocks, AR_THREADS, 0, s>>>(mc, pads, rank, world, slot0, n_vec4, scale);
+    return 1;
 }
 
 }  // namespace gg

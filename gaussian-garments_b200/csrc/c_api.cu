@@ -563,7 +563,7 @@ int gg_nvls_allreduce_f32(void* multicast_base, const void* signal_pads_dev, int
     if (world_size > 32) return fail(GG_E_BADARG, "world_size > 32 not supported");
     if (elem_offset < 0 || elem_count < 0 || (elem_offset & 3) || (elem_count & 3))
         return fail(GG_E_ALIGN, "elem_offset and elem_count must be multiples of 4 floats");
-    if (num_blocks < 1 || num_blocks > 592 || pad_slot0 < 0) return fail(GG_E_BADARG, "bad num_blocks / pad_slot0");
+    if (num_blocks < 1 || num_blocks > 148 || pad_slot0 < 0) return fail(GG_E_BADARG, "bad num_blocks / pad_slot0");
     float* mc = reinterpret_cast<float*>(multicast_base) + elem_offset;
     if (!aligned16(mc)) return fail(GG_E_ALIGN, "multicast pointer not 16-byte aligned");
     GG_CUDA(cudaSetDevice(device));

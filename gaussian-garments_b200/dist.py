@@ -88,12 +88,10 @@ class GradBucket:
         self._hdl = hdl
         self._mc_ptr = mc
         self._pads_dev = int(hdl.signal_pad_ptrs_dev)
-        if int(hdl.signal_pad_size) // 4 < 2 * self.world:
-            raise RuntimeError("signal pad too small")
-        # grid widths of the data kernel (bytes in flight set its bandwidth); one pad slot range per concurrent instance
-        nb = os.environ.get("GG_AR_BLOCKS", "64,128").split(",")
-        self._blocks = (int(nb[0]), int(nb[-1]))
-        self._slot0 = (0, self.world)
+        pad_words = int(hdl.signal_pad_size) // 4
+        blocks = max(2, min(72, pad_words // self.world))      # one pad word per (block, peer)
+        self._blocks = (max(1, blocks // 3), max(1, blocks - blocks // 3))      # (immediate, deferred)
+        self._slot0 = (0, self._blocks[0] * self.world)
         self.flat = flat
         self.impl = "nvls_multimem"
         torch.cuda.synchronize(dev)

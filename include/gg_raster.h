@@ -211,9 +211,8 @@ int gg_cast_rays_from_point(int32_t num_vertices, int32_t num_faces, int32_t num
  * on return -- stream-ordered -- elements [elem_offset, elem_offset + elem_count) of EVERY rank's buffer hold
  * scale * (sum over ranks).  One kernel per rank: multimem.ld_reduce (the switch adds) + multimem.st (the switch
  * broadcasts); rank r reduces the r-th 1/world slice.  signal_pads_dev: device array of world_size pointers to the
- * ranks' uint32 signal pads (zero-initialised; world_size words from pad_slot0 are used -- give concurrent calls on
- * different streams disjoint ranges).  Three launches: a one-warp entry barrier, the data kernel (num_blocks x 512
- * threads), a one-warp exit barrier.  All ranks must call with identical arguments, in the same order.            */
+ * ranks' uint32 signal pads (zero-initialised; num_blocks * world_size words from pad_slot0 are used -- give concurrent
+ * calls on different streams disjoint ranges).  All ranks must call with identical arguments, in the same order.   */
 int gg_nvls_allreduce_f32(void* multicast_base, const void* signal_pads_dev, int32_t rank, int32_t world_size,
                           int64_t elem_offset, int64_t elem_count, float scale, int32_t pad_slot0, int32_t num_blocks,
                           int device, void* stream);
