@@ -77,6 +77,10 @@ def parse():
     ap.add_argument("--height", type=int, default=HEIGHT)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="no CUDA graphs: every step through Python")
+    ap.add_argument("--exchange", choices=["around", "ingraph"], default=os.environ.get("GG_BENCH_EXCHANGE", "around"),
+                    help="multi-GPU graph mode: 'around' = the step is a graph, both exchanges are issued eagerly right "
+                         "behind it (SH block overlaps the geometry block AND the next projection/binning, joined by the "
+                         "device-side colour gate); 'ingraph' = exchanges captured inside the step graph")
     ap.add_argument("--cpu-views", type=int, default=3, help="views timed for the cpu_baseline block")
     return ap.parse_args()
 
@@ -261,15 +265,16 @@ def main():
     # ---------------- CUDA graphs: the whole step (forward, fused L1, backward, exchange) as ONE launch --------------
     # The public API is called unchanged inside a torch.cuda.graph capture (rasterizer.py: the sync-free hinted forward
     # needs no host round trip; instance-capacity overflow is recorded on the device and checked after the loops).
-    # Two graphs, one per input slot: slot k owns a ground-truth buffer and a camera (view / projection / centre).
+    # One graph per input slot (NS = 3): slot k owns a ground-truth buffer and a camera (view / projection / centre).
     import copy
     from gaussian_garments_b200 import rasterizer as _rast
-    slot_gt = [torch.empty(3, H, W, device=dev) for _ in range(2)]
-    slot_u8 = [torch.zeros(3, H, W, dtype=torch.uint8, device=dev) for _ in range(2)]     # e2e: the H2D payload
-    slot_cam = [[torch.empty(4, 4, device=dev), torch.empty(4, 4, device=dev), torch.empty(3, device=dev)] for _ in range(2)]
-    slot_loss = [torch.zeros(1, device=dev) for _ in range(2)]
+    NS = 3              # input slots: step i computes on slot i%NS while the host stages i+1 and reads back i-2
+    slot_gt = [torch.empty(3, H, W, device=dev) for _ in range(NS)]
+    slot_u8 = [torch.zeros(3, H, W, dtype=torch.uint8, device=dev) for _ in range(NS)]     # e2e: the H2D payload
+    slot_cam = [[torch.empty(4, 4, device=dev), torch.empty(4, 4, device=dev), torch.empty(3, device=dev)] for _ in range(NS)]
+    slot_loss = [torch.zeros(1, device=dev) for _ in range(NS)]
     slot_camobj = []
-    for k in range(2):
+    for k in range(NS):
         c = copy.copy(cams[0])
         c.world_view_transform, c.full_proj_transform, c.camera_center = slot_cam[k]
         slot_camobj.append(c)
@@ -285,15 +290,23 @@ def main():
         """One step on slot k.  Multi-GPU: the deferred (SH) block of the PREVIOUS step is exchanged on the side stream
         first and joins at this forward's colour kernel; the immediate block is exchanged after the backward.
         from_u8 (end-to-end loop): the loss reads the slot's 8-bit image, just copied from the host, directly."""
-        if world > 1:
+        if world > 1 and not around:
             bucket.exchange_deferred_async()
         loss = step(0, slot_u8[k] if from_u8 else slot_gt[k], slot_camobj[k], collective=False)
         if world > 1:
             bucket.adopt()
-            bucket.exchange_immediate()
+            if not around:
+                bucket.exchange_immediate()
         slot_loss[k].copy_(loss.detach().reshape(1))
 
+    def exchanges_behind_graph():
+        """'around' mode: both exchanges right behind the replayed step; the SH block runs on the side stream and the
+        NEXT replay's colour stage waits for it on the device (dist.GradBucket.use_device_gate)."""
+        bucket.exchange_immediate()
+        bucket.exchange_deferred_async()
+
     graphs, graph_note, launches_per_replay = None, None, 0
+    around = False
     if args.eager:
         graph_note = "disabled (--eager)"
     elif not same_fov:
@@ -302,22 +315,25 @@ def main():
         graph_note = f"disabled: exchange runs through the process group ({bucket.nvls_error})"
     else:
         try:
-            for k in range(2):
-                load_slot(k, (k * world + rank) % N_CAMS, gt_dev[k])
+            for k in range(NS):
+                load_slot(k, (k * world + rank) % N_CAMS, gt_dev[k % 2])
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):                  # eager warm-up on a side stream (sizes the capacity hints)
                 for i in range(max(3, min(args.warmup, 2 * N_CAMS))):
-                    load_slot(i % 2, (i * world + rank) % N_CAMS)
-                    slot_body(i % 2)
+                    load_slot(i % NS, (i * world + rank) % N_CAMS)
+                    slot_body(i % NS)
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             if world > 1:
                 bucket.wait()
                 dist.barrier()
+                if args.exchange == "around":
+                    around = True
+                    bucket.use_device_gate(True)
             graphs, graphs_u8 = [], []
             for from_u8, dst in ((False, graphs), (True, graphs_u8)):
-                for k in range(2):
+                for k in range(NS):
                     _capi.launch_count(reset=True)
                     g_ = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g_):
@@ -326,8 +342,14 @@ def main():
                     dst.append(g_)
             torch.cuda.synchronize()
             graph_note = "whole step per launch; one graph per input slot (x2: device-resident float GT / 8-bit GT from the host)"
+            if world > 1:
+                graph_note += ("; exchanges issued eagerly behind each replay, device-side colour gate" if around
+                               else "; exchanges captured inside the graph")
         except Exception as e:                             # never lose the bench line to a capture problem
             graphs = None
+            if around:
+                around = False
+                bucket.use_device_gate(False)
             graph_note = f"capture failed, eager fallback: {type(e).__name__}: {str(e)[:200]}"
             try:
                 torch.cuda.synchronize()
@@ -336,13 +358,17 @@ def main():
 
     def run_step(i, gt_src=None, last=False):
         """Step i through a graph replay (or eagerly): camera of this rank into slot i%2, replay, drain at the end."""
-        k = i % 2
+        k = i % NS
         ci = (i * world + rank) % N_CAMS
         if graphs is None:
-            return step(i, gt_dev[k] if gt_src is None else gt_src, cams[ci], drain=last)
+            return step(i, gt_dev[i % 2] if gt_src is None else gt_src, cams[ci], drain=last)
         load_slot(k, ci)
         graphs[k].replay()
-        if last and world > 1:
+        if around:
+            exchanges_behind_graph()
+            if last:
+                bucket.wait()
+        elif last and world > 1:
             bucket.exchange_deferred_async()               # the final step's SH block has no successor graph
             bucket.wait()
         return slot_loss[k]
@@ -393,32 +419,36 @@ def main():
     # happens inside the timed region.  The loss of step i is copied D2H asynchronously and read on the host while step
     # i+1 is already enqueued, so the GPU never waits for Python; every step's result is read inside the timed region.
     copy_stream = torch.cuda.Stream(device=dev)
-    ready = [torch.cuda.Event() for _ in range(2)]
-    loss_host = torch.zeros(2).pin_memory()
-    done = [torch.cuda.Event() for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(NS)]
+    loss_host = torch.zeros(NS).pin_memory()
+    done = [torch.cuda.Event() for _ in range(NS)]
 
     def prefetch(i):
         ci = (i * world + rank) % N_CAMS
         with torch.cuda.stream(copy_stream):
-            slot_u8[i % 2].copy_(gt_pinned[i % 2], non_blocking=True)
-            for dst, src in zip(slot_cam[i % 2], cam_pinned[ci]):
+            slot_u8[i % NS].copy_(gt_pinned[i % 2], non_blocking=True)
+            for dst, src in zip(slot_cam[i % NS], cam_pinned[ci]):
                 dst.copy_(src, non_blocking=True)
-            ready[i % 2].record(copy_stream)
+            ready[i % NS].record(copy_stream)
 
     def e2e_run(n):
         vals = []
         cur = torch.cuda.current_stream()
         prefetch(0)
         for i in range(n):
-            k = i % 2
+            k = i % NS
             cur.wait_event(ready[k])
             if i + 1 < n:
-                if i >= 1:
-                    copy_stream.wait_event(done[(i - 1) % 2])      # slot (i+1)%2 is free once step i-1 has finished
+                if i + 1 >= NS:
+                    copy_stream.wait_event(done[(i + 1 - NS) % NS])    # slot (i+1)%NS is free once step i+1-NS has finished
                 prefetch(i + 1)
             if graphs is not None:
                 graphs_u8[k].replay()
-                if i == n - 1 and world > 1:
+                if around:
+                    exchanges_behind_graph()
+                    if i == n - 1:
+                        bucket.wait()
+                elif i == n - 1 and world > 1:
                     bucket.exchange_deferred_async()
                     bucket.wait()
                 loss = slot_loss[k]
@@ -426,11 +456,13 @@ def main():
                 loss = step(i, slot_u8[k], slot_camobj[k], drain=(i == n - 1))
             loss_host[k:k + 1].copy_(loss.detach().reshape(1), non_blocking=True)   # D2H read of the result
             done[k].record(cur)
-            if i >= 1:
-                done[(i - 1) % 2].synchronize()
-                vals.append(float(loss_host[(i - 1) % 2]))
-        done[(n - 1) % 2].synchronize()
-        vals.append(float(loss_host[(n - 1) % 2]))
+            if i >= NS - 1:                                        # read step i-2's loss: two steps stay queued on the GPU
+                j = i - (NS - 1)
+                done[j % NS].synchronize()
+                vals.append(float(loss_host[j % NS]))
+        for j in range(max(0, n - (NS - 1)), n):
+            done[j % NS].synchronize()
+            vals.append(float(loss_host[j % NS]))
         assert len(vals) == n and all(math.isfinite(v) for v in vals)
         return vals
 
@@ -458,6 +490,10 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * e_steps / float(t.item())
     graph_overflowed, graph_max_k = _rast.graph_overflow(dev) if graphs is not None else (False, 0)
+    gate_timed_out = None
+    if around:
+        gate_timed_out = bucket.device_gate.timed_out()
+        bucket.use_device_gate(False)                      # everything below is eager again: stream-event gate
 
     # ---------------- the exchange, checked and timed in isolation (all ranks; outside the timed regions) -------------
     collective = None
@@ -558,7 +594,9 @@ def main():
                         "p90": step_ms[(len(step_ms) * 9) // 10]},
             "wall_s_timed_region_incl_flush": wall, "host_ms_per_step": 1e3 * host_s / args.steps,
             "cuda_graphs": {"mode": graph_note, "launches_per_replay": launches_per_replay,
-                            "instance_overflow": graph_overflowed, "max_num_rendered": graph_max_k},
+                            "instance_overflow": graph_overflowed, "max_num_rendered": graph_max_k,
+                            "exchange": (("around" if around else "ingraph") if world > 1 and graphs is not None else None),
+                            "colour_gate_timed_out": gate_timed_out},
             "e2e_loss_first_last": [e2e_vals[0], e2e_vals[-1]],
             "forward_stats": dict(_rasterizer_stats()),
             "clocks": clocks, "gpu_launches": int(launches),
@@ -566,7 +604,7 @@ def main():
                     "what": "pinned-host 8-bit GT frame + camera matrices copied H2D every step (copy stream, overlapping the "
                             "previous step's compute), dequantised inside the fused L1 kernels, public GaussianRasterizer API fwd + fused "
                             "L1 + bwd (CUDA-graph replay of that call sequence unless --eager), every step's loss copied D2H "
-                            "(async, read one step later); wall clock, max over ranks",
+                            "(async, read two steps later: three input slots); wall clock, max over ranks",
                     "steps": e_steps, "h2d_gbs_measured": h2d_gbs},
             "roofline": roofline}
     if collective is not None:

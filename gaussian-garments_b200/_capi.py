@@ -156,7 +156,8 @@ def load():
         lib.gg_forward_project.argtypes = [P(GGView), P(GGInputs), vp, vp, vp, vp, i32, vp]
         lib.gg_forward_color.argtypes = [P(GGView), P(GGInputs), vp, vp, i32, vp]
         lib.gg_forward_render.argtypes = [P(GGView), P(GGInputs), vp, vp, vp, vp, i64, i64, vp, vp, vp, vp, vp, i32, vp]
-        lib.gg_forward_render_late_color.argtypes = [P(GGView), P(GGInputs), vp, vp, vp, vp, i64, i64, vp, vp, vp, vp, vp, vp, i32, vp]
+        lib.gg_forward_render_late_color.argtypes = [P(GGView), P(GGInputs), vp, vp, vp, vp, i64, i64, vp, vp, vp, vp, vp, vp, vp, i32, vp]
+        lib.gg_gate_signal.argtypes = [vp, i32, vp]
         lib.gg_forward_overflow_check.argtypes = [P(GGView), vp, i64, vp, i32, vp]
         lib.gg_backward.argtypes = [P(GGView), P(GGInputs), vp, vp, i64, vp, vp, vp] + [vp] * 11 + [i32, vp]
         lib.gg_mark_visible.argtypes = [C.c_int32, vp, vp, vp, vp, i32, vp]
@@ -183,7 +184,7 @@ def load():
         lib.gg_kernel_times.argtypes = [P(C.c_float)]
         for name in ("gg_forward_workspace_bytes", "gg_instance_workspace_bytes", "gg_backward_workspace_bytes",
                      "gg_forward_project", "gg_forward_color", "gg_forward_render", "gg_backward",
-                     "gg_forward_overflow_check", "gg_forward_render_late_color", "gg_mark_visible", "gg_debug_read_geom", "gg_debug_read_binning", "gg_debug_lazy_phase_counters", "gg_kernel_timing", "gg_kernel_times",
+                     "gg_forward_overflow_check", "gg_forward_render_late_color", "gg_gate_signal", "gg_mark_visible", "gg_debug_read_geom", "gg_debug_read_binning", "gg_debug_lazy_phase_counters", "gg_kernel_timing", "gg_kernel_times",
                      "gg_mesh_bind_workspace_bytes", "gg_mesh_bind_forward", "gg_mesh_bind_backward",
                      "gg_mesh_bind_forward_ex", "gg_mesh_bind_backward_ex", "gg_cast_rays_workspace_bytes",
                      "gg_cast_rays_from_point", "gg_nvls_allreduce_f32",
@@ -204,7 +205,7 @@ def check(rc: int, what: str):
 EXPORTED_SYMBOLS = [
     "gg_abi_version", "gg_version", "gg_last_error", "gg_launch_count", "gg_forward_workspace_bytes",
     "gg_instance_workspace_bytes", "gg_backward_workspace_bytes", "gg_forward_project", "gg_forward_color",
-    "gg_forward_render", "gg_forward_render_late_color", "gg_forward_overflow_check", "gg_backward", "gg_mark_visible", "gg_debug_read_geom", "gg_debug_read_binning",
+    "gg_forward_render", "gg_forward_render_late_color", "gg_gate_signal", "gg_forward_overflow_check", "gg_backward", "gg_mark_visible", "gg_debug_read_geom", "gg_debug_read_binning",
     "gg_debug_lazy_phase_counters", "gg_kernel_timing",
     "gg_kernel_count", "gg_kernel_name", "gg_kernel_times", "gg_mesh_bind_workspace_bytes", "gg_mesh_bind_forward",
     "gg_mesh_bind_backward", "gg_mesh_bind_forward_ex", "gg_mesh_bind_backward_ex", "gg_cast_rays_workspace_bytes",

@@ -92,6 +92,35 @@ nvls_allreduce_kernel(float* __restrict__ mc, uint32_t* const* __restrict__ pads
     cross_rank_barrier<true>(pads, rank, world, slot0);       // every rank's slice has landed everywhere
 }
 
+// ---- device-side gate (CUDA-graph friendly cross-stream dependency) -------------------------------------------------
+// gate[0] = G: how many gated colour stages have started; gate[1] = X: how many deferred exchanges have completed;
+// gate[2] = timeout flag.  The k-th gated forward may read the SH coefficients once exchanges 1..k-1 are done (X >= k-1).
+// A stream-event wait cannot cross a graph boundary; one spinning WARP can (a whole grid parked on the flag could starve
+// the exchange kernel of SM slots, one warp cannot).  The spin gives up after ~1 s and raises the timeout flag.
+__global__ void __launch_bounds__(32) gate_wait_kernel(uint32_t* __restrict__ gate) {
+    if (threadIdx.x == 0) {
+        const uint32_t k = atomicAdd(&gate[0], 1u) + 1u;
+        uint32_t spins = 0;
+        while (*reinterpret_cast<volatile uint32_t*>(&gate[1]) + 1u < k) {
+            __nanosleep(200);
+            if (++spins > (1u << 22)) { atomicOr(&gate[2], 1u); break; }
+        }
+        __threadfence();
+    }
+}
+__global__ void gate_signal_kernel(uint32_t* __restrict__ gate) {
+    __threadfence();
+    atomicAdd(&gate[1], 1u);
+}
+int launch_gate_wait(uint32_t* gate, cudaStream_t s) {
+    gate_wait_kernel<<<1, 32, 0, s>>>(gate);
+    return 1;
+}
+int launch_gate_signal(uint32_t* gate, cudaStream_t s) {
+    gate_signal_kernel<<<1, 1, 0, s>>>(gate);
+    return 1;
+}
+
 int launch_nvls_allreduce(float* mc, uint32_t* const* pads, int rank, int world, int slot0, int64_t n_vec4, float scale,
                           int blocks, cudaStream_t s) {
     if (n_vec4 <= 0) return 0;

@@ -227,7 +227,7 @@ int gg_forward_color(const gg_view* view, const gg_inputs* in, void* geom_ws, co
 static int forward_render_impl(const gg_view* view, const gg_inputs* in, const void* geom_ws, void* tile_ws, void* key_ws,
                                void* record_ws, int64_t instance_capacity, int64_t max_tile_instances, void* image_ws,
                                const int32_t* radii, float* out_color, float* out_depth, float* out_alpha, bool late_color,
-                               void* color_gate_event, int device, void* stream) {
+                               void* color_gate_event, uint32_t* color_gate_words, int device, void* stream) {
     if (int rc = check_view(view)) return rc;
     if (int rc = check_inputs(view, in)) return rc;
     if (!geom_ws || !tile_ws || !key_ws || !record_ws || !image_ws || !out_color || !out_depth || !out_alpha)
@@ -267,6 +267,7 @@ static int forward_render_impl(const gg_view* view, const gg_inputs* in, const v
     }
     auto colours = [&]() -> int {                  // late-colour mode: SH -> RGB behind the gate, after the sort
         if (color_gate_event) GG_CUDA(cudaStreamWaitEvent(s, (cudaEvent_t)color_gate_event, 0));
+        if (color_gate_words) g_launches += launch_gate_wait(color_gate_words, s);      // device-side gate (graph replays)
         { ScopedKernelTimer kt(K_SHCOLOR, s); g_launches += launch_sh_color(*view, *in, g, radii, s); }
         return after_launch(view, s, "sh_color_kernel");
     };
@@ -303,15 +304,26 @@ int gg_forward_render(const gg_view* view, const gg_inputs* in, const void* geom
                       const int32_t* radii, float* out_color, float* out_depth, float* out_alpha, int device,
                       void* stream) {
     return forward_render_impl(view, in, geom_ws, tile_ws, key_ws, record_ws, instance_capacity, max_tile_instances,
-                               image_ws, radii, out_color, out_depth, out_alpha, false, nullptr, device, stream);
+                               image_ws, radii, out_color, out_depth, out_alpha, false, nullptr, nullptr, device, stream);
 }
 
 int gg_forward_render_late_color(const gg_view* view, const gg_inputs* in, void* geom_ws, void* tile_ws, void* key_ws,
                                  void* record_ws, int64_t instance_capacity, int64_t max_tile_instances, void* image_ws,
                                  const int32_t* radii, float* out_color, float* out_depth, float* out_alpha,
-                                 void* color_gate_event, int device, void* stream) {
+                                 void* color_gate_event, uint32_t* color_gate_words, int device, void* stream) {
     return forward_render_impl(view, in, geom_ws, tile_ws, key_ws, record_ws, instance_capacity, max_tile_instances,
-                               image_ws, radii, out_color, out_depth, out_alpha, true, color_gate_event, device, stream);
+                               image_ws, radii, out_color, out_depth, out_alpha, true, color_gate_event, color_gate_words,
+                               device, stream);
+}
+
+int gg_gate_signal(uint32_t* gate_words, int device, void* stream) {
+    if (!gate_words) return fail(GG_E_BADARG, "gate_words is NULL");
+    GG_CUDA(cudaSetDevice(device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const gg_view* view = nullptr;
+    g_launches += launch_gate_signal(gate_words, s);
+    GG_AFTER("gate_signal_kernel");
+    return 0;
 }
 
 int gg_forward_overflow_check(const gg_view* view, const void* tile_ws, int64_t instance_capacity, uint32_t* flag2,

@@ -178,6 +178,8 @@ int launch_mesh_bind_backward(int F, int N, const float* verts, const int32_t* f
                               const float* g_rot, float* gF, float* g_verts, float* gl_xyz, float* gl_scal, float* gl_rot,
                               cudaStream_t s);
 
+int launch_gate_wait(uint32_t* gate, cudaStream_t s);
+int launch_gate_signal(uint32_t* gate, cudaStream_t s);
 int launch_nvls_allreduce(float* mc, uint32_t* const* pads, int rank, int world, int slot0, int64_t n_vec4, float scale,
                           int blocks, cudaStream_t s);
 size_t vis_workspace_bytes(int64_t V, int64_t capacity);

@@ -69,6 +69,7 @@ class GradBucket:
             self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
         self.comm_stream = None
         self.late_done = None
+        self.device_gate = None
         if dev.type == "cuda" and self.world > 1 and self.split < total:
             self.comm_stream = torch.cuda.Stream(device=dev, priority=-1)
             self.late_done = torch.cuda.Event()
@@ -189,12 +190,32 @@ class GradBucket:
         ready = torch.cuda.Event()
         ready.record(cur)
         self.comm_stream.wait_event(ready)
+        from . import rasterizer, _capi
+        di = self.device.index if self.device.index is not None else torch.cuda.current_device()
         with torch.cuda.stream(self.comm_stream):
             self._reduce_range(self.split, self.numel, 1)
+            if self.device_gate is not None:                # graph replays: advance X behind the exchange
+                _capi.check(_capi.load().gg_gate_signal(self.device_gate.words.data_ptr(), di,
+                                                        self.comm_stream.cuda_stream), "gg_gate_signal")
             self.late_done.record(self.comm_stream)
+        if self.device_gate is None:
+            rasterizer.COLOR_GATE[di] = self.late_done      # next forward: SH -> RGB waits, projection/binning do not
+
+    def use_device_gate(self, on: bool = True):
+        """Switch the colour gate to its device-side form (needed when the step is replayed as a CUDA graph while the
+        exchanges are issued eagerly around it): every forward then takes a ticket, every deferred exchange advances
+        the counter -- they must alternate strictly.  `on=False` returns to stream events."""
         from . import rasterizer
         di = self.device.index if self.device.index is not None else torch.cuda.current_device()
-        rasterizer.COLOR_GATE[di] = self.late_done          # next forward: SH -> RGB waits, projection/binning do not
+        torch.cuda.synchronize(self.device)
+        if on:
+            if self.device_gate is None:
+                self.device_gate = rasterizer.DeviceGate(self.device)
+            self.device_gate.reset()
+            rasterizer.COLOR_GATE[di] = self.device_gate
+        else:
+            self.device_gate = None
+            rasterizer.COLOR_GATE.pop(di, None)
 
     def wait(self):
         """Make the current stream wait for the deferred block (call before consuming those gradients)."""

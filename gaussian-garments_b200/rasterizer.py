@@ -56,6 +56,19 @@ DEBUG_CAPTURE = None    # tests set this to a dict: the next forward leaves its 
 COLOR_GATE = {}
 
 
+class DeviceGate:
+    """Graph-replay form of the colour gate: three device words {G, X, timeout} (see gg_forward_render_late_color)."""
+
+    def __init__(self, device):
+        self.words = torch.zeros(4, dtype=torch.int32, device=device)
+
+    def reset(self):
+        self.words.zero_()
+
+    def timed_out(self) -> bool:
+        return bool(int(self.words[2]) != 0)
+
+
 class GradSink:
     """Destination of one leaf tensor's gradient inside a flat bucket (dist.GradBucket): when a leaf carries
     one (attribute `_gg_sink` on the tensor OBJECT -- never keyed by address, so a recycled allocation cannot
@@ -214,7 +227,9 @@ class _RasterizeGaussians(torch.autograd.Function):
                         _capi.check(lib.gg_forward_render_late_color(
                             C.byref(view), C.byref(inputs), geom_ws.data_ptr(), tile_ws.data_ptr(), kw.data_ptr(),
                             rw.data_ptr(), cap, mt, image_ws.data_ptr(), _ptr(radii), color.data_ptr(), depth.data_ptr(),
-                            alpha.data_ptr(), None if late["gate"] is None else late["gate"].cuda_event, di, sp),
+                            alpha.data_ptr(),
+                            late["gate"].cuda_event if isinstance(late["gate"], torch.cuda.Event) else None,
+                            late["gate"].words.data_ptr() if isinstance(late["gate"], DeviceGate) else None, di, sp),
                             "gg_forward_render_late_color")
                         late["gate"] = None          # a retry after an overflow must not wait again (already passed)
                     else:
@@ -245,6 +260,9 @@ class _RasterizeGaussians(torch.autograd.Function):
                     # overlaps with projection + emit + sort; without a hint it simply waits here.
                     late["on"] = gate is not None and hint is not None
                     late["gate"] = gate if late["on"] else None
+                    if isinstance(gate, DeviceGate) and not late["on"]:
+                        raise RuntimeError("gaussian-garments_b200: a device colour gate needs the hinted (late-colour) "
+                                           "forward: run one eager forward of this shape first")
                     if not late["on"]:
                         if gate is not None:
                             stream.wait_event(gate)

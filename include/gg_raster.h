@@ -113,11 +113,15 @@ int gg_forward_render(const gg_view* view, const gg_inputs* in, const void* geom
 /* Same as gg_forward_render, but the colour stage (gg_forward_color must NOT have been called) runs AFTER instance
  * emission and the per-tile sort, behind `color_gate_event` (a cudaEvent_t, may be NULL): the only consumer of the SH
  * coefficients then waits for the previous step's SH-gradient exchange (multi-GPU, dist.py) while projection, emission
- * and sorting of this view are already executing; colours are then scattered into the packed records.            */
+ * and sorting of this view are already executing; colours are then scattered into the packed records.
+ * color_gate_words (may be NULL) is the graph-replay form of the same gate: three device words {G, X, timeout}; the
+ * colour stage first runs a one-warp kernel that takes ticket k = ++G and waits until X >= k - 1, where X is advanced by
+ * gg_gate_signal() enqueued behind each SH-gradient exchange -- a dependency that survives CUDA-graph boundaries.   */
 int gg_forward_render_late_color(const gg_view* view, const gg_inputs* in, void* geom_ws, void* tile_ws, void* key_ws,
                                  void* record_ws, int64_t instance_capacity, int64_t max_tile_instances, void* image_ws,
                                  const int32_t* radii, float* out_color, float* out_depth, float* out_alpha,
-                                 void* color_gate_event, int device, void* stream);
+                                 void* color_gate_event, uint32_t* color_gate_words, int device, void* stream);
+int gg_gate_signal(uint32_t* gate_words, int device, void* stream);
 
 /* ---- sync-free operation (CUDA graphs): upstream blocks on a D2H copy of num_rendered in the middle of every
  * forward; when the instance workspaces are sized from an earlier call instead, this records on the
