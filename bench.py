@@ -551,6 +551,33 @@ def main():
             acc[k] = acc.get(k, 0.0) + v / reps
         Ks.append(_capi_last_K())
     _capi.kernel_timing(False)
+    # secondary number (not the metric): the loss the reference's stages actually run, lambda_dssim = 0.2
+    # (s2_registration.py:259-260: l1*(1-lambda) + 1 - ssim*lambda) through the fused photometric op, eager steps
+    ssim_line = None
+    try:
+        def ssim_step(i):
+            cam = cams[(i * world + rank) % N_CAMS]
+            color, _, _, _ = dgr.GaussianRasterizer(raster_settings=settings(cam))(
+                means3D=params[0], means2D=torch.zeros_like(params[0], requires_grad=True), shs=params[4],
+                colors_precomp=None, opacities=params[3], scales=params[1], rotations=params[2], cov3D_precomp=None)
+            bucket.zero()
+            gg.photometric_loss(color, gt_dev[i % 2], None, 0.2)[0].backward()
+        for i in range(3):
+            ssim_step(i)
+        torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_ssim = 20
+        s0.record()
+        for i in range(n_ssim):
+            ssim_step(i)
+        s1.record()
+        torch.cuda.synchronize()
+        ssim_ms = s0.elapsed_time(s1) / n_ssim
+        ssim_line = {"what": "same step with the reference's training loss, lambda_dssim = 0.2 (fused L1 + SSIM forward/backward "
+                             "kernels), eager, device-resident inputs, no L2 flush; secondary, not the metric",
+                     "ms_per_step": round(ssim_ms, 4), "views_per_s": round(1e3 / ssim_ms, 1), "steps": n_ssim}
+    except Exception as e:
+        ssim_line = {"error": f"{type(e).__name__}: {str(e)[:160]}"}
     K = int(sum(Ks) / len(Ks))
     gx, gy = (W + 15) // 16, (H + 15) // 16
     ab = algorithmic_bytes(args.gaussians, K, W * H, gx * gy)
@@ -598,6 +625,7 @@ def main():
                             "exchange": (("around" if around else "ingraph") if world > 1 and graphs is not None else None),
                             "colour_gate_timed_out": gate_timed_out},
             "e2e_loss_first_last": [e2e_vals[0], e2e_vals[-1]],
+            "with_ssim_loss": ssim_line,
             "forward_stats": dict(_rasterizer_stats()),
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,

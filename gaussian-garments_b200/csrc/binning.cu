@@ -109,9 +109,12 @@ constexpr int SORT_THREADS = 256;
 constexpr uint32_t SORT_SMEM_KEYS = 4096;   // default: 32 KB of keys per CTA (7 CTAs/SM)
 constexpr uint32_t SORT_SMEM_KEYS_MAX = 24576;   // 192 KB dynamic variant for dense scenes; beyond: L2/global
 
-// Shared-memory variant with ~4x fewer CTA barriers: every step whose comparators stay inside an
-// aligned 64-key block (all of k <= 64, and the stride <= 32 tail of every later merge) is done by
-// ONE warp per block with __syncwarp only; __syncthreads is needed just around the long strides.
+// Shared-memory variant with ~4x fewer CTA barriers: every step whose comparators stay inside an aligned 64-key block
+// (all of k <= 64, and the stride <= 32 tail of every later merge) is done by ONE warp per block IN REGISTERS: lane l
+// holds keys l and l + 32 of the block, stride 32 is an in-thread exchange, shorter strides are shfl_xor exchanges.
+// (The first version ran those steps through shared memory with __syncwarp: a warp's 64-bit accesses at stride < 16 keys
+//  span 512 B for 256 B of data -- ncu: 4.5 M bank conflicts on 13.5 M shared wavefronts, LSU data pipe at 67 %.)
+// __syncthreads is needed just around the long strides, which are conflict-free (consecutive lanes, consecutive keys).
 __device__ __forceinline__ void cs_smem(uint64_t* a, uint32_t lo, uint32_t hi, uint32_t n) {
     if (hi < n) {
         const uint64_t x = a[lo], y = a[hi];
@@ -121,30 +124,60 @@ __device__ __forceinline__ void cs_smem(uint64_t* a, uint32_t lo, uint32_t hi, u
         }
     }
 }
-__device__ __forceinline__ void warp_half_cleaners(uint64_t* a, uint32_t base, uint32_t n, uint32_t lane, int ld_from) {
-    for (int ld = ld_from; ld >= 0; ld--) {          // strides 2^ld ... 1 inside one 64-key block
-        const uint32_t lo = base + (((lane >> ld) << (ld + 1)) | (lane & ((1u << ld) - 1u)));
-        cs_smem(a, lo, lo + (1u << ld), n);
-        __syncwarp();
+__device__ __forceinline__ uint64_t shfl_xor_u64(uint64_t v, int m) {
+    const uint32_t lo = __shfl_xor_sync(0xffffffffu, (uint32_t)v, m), hi = __shfl_xor_sync(0xffffffffu, (uint32_t)(v >> 32), m);
+    return ((uint64_t)hi << 32) | lo;
+}
+__device__ __forceinline__ uint64_t keep(uint64_t mine, uint64_t other, bool want_min) {
+    return (want_min == (other < mine)) ? other : mine;      // ties: either copy is the same key
+}
+// strides 2^ld_from ... 1 inside one 64-key block held as (r0 = key[lane], r1 = key[lane + 32])
+__device__ __forceinline__ void reg_half_cleaners(uint64_t& r0, uint64_t& r1, uint32_t lane, int ld_from) {
+    if (ld_from >= 5) {
+        const uint64_t lo = r0 < r1 ? r0 : r1, hi = r0 < r1 ? r1 : r0;
+        r0 = lo;
+        r1 = hi;
+        ld_from = 4;
+    }
+#pragma unroll
+    for (int ld = 4; ld >= 0; ld--) {
+        if (ld <= ld_from) {
+            const bool lower = (lane & (1u << ld)) == 0u;
+            r0 = keep(r0, shfl_xor_u64(r0, 1 << ld), lower);
+            r1 = keep(r1, shfl_xor_u64(r1, 1 << ld), lower);
+        }
     }
 }
-__device__ void bitonic_sort_smem(uint64_t* a, uint32_t n) {
+constexpr uint64_t KEY_INF = ~0ull;
+// `src` (optional): the unsorted keys are still in global memory -- the first six merge levels read them straight into
+// registers and only the 64-key sorted runs are written to shared memory.
+__device__ void bitonic_sort_smem(uint64_t* a, uint32_t n, const uint64_t* __restrict__ src = nullptr) {
     uint32_t P = 1, lp = 0;
     while (P < n) { P <<= 1; lp++; }
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = SORT_THREADS / 32;
-    // phase 1: merges of size 2..64, warp-local
+    // phase 1: merges of size 2..64, warp-local, in registers (keys beyond n are +inf and never move down)
     for (uint32_t base = warp * 64; base < n; base += nwarps * 64) {
-        const uint32_t lk_max = lp < 6 ? lp : 6;
-        for (uint32_t lk = 1; lk <= lk_max; lk++) {
-            const uint32_t k = 1u << lk, hk = k >> 1;
-            const uint32_t blk = lane >> (lk - 1), w = lane & (hk - 1);
-            cs_smem(a, base + (blk << lk) + w, base + (blk << lk) + k - 1 - w, n);
-            __syncwarp();
-            if (lk >= 2) warp_half_cleaners(a, base, n, lane, (int)lk - 2);
+        const uint32_t i0 = base + lane, i1 = base + lane + 32;
+        uint64_t r0 = i0 < n ? (src ? src[i0] : a[i0]) : KEY_INF;
+        uint64_t r1 = i1 < n ? (src ? src[i1] : a[i1]) : KEY_INF;
+#pragma unroll
+        for (int lk = 1; lk <= 5; lk++) {
+            const bool lower = (lane & (1u << (lk - 1))) == 0u;          // flip step: partner = e ^ (2^lk - 1)
+            r0 = keep(r0, shfl_xor_u64(r0, (1 << lk) - 1), lower);
+            r1 = keep(r1, shfl_xor_u64(r1, (1 << lk) - 1), lower);
+            if (lk >= 2) reg_half_cleaners(r0, r1, lane, lk - 2);
         }
+        {   // lk = 6: partner of (lane, r) is (lane ^ 31, r ^ 1); the r = 0 copy is the lower one
+            const uint64_t q0 = shfl_xor_u64(r1, 31), q1 = shfl_xor_u64(r0, 31);
+            r0 = keep(r0, q0, true);
+            r1 = keep(r1, q1, false);
+            reg_half_cleaners(r0, r1, lane, 4);
+        }
+        if (i0 < n) a[i0] = r0;
+        if (i1 < n) a[i1] = r1;
     }
     __syncthreads();
-    // phase 2: merges of size 128..P: long strides CTA-wide, stride <= 32 tail warp-local
+    // phase 2: merges of size 128..P: long strides CTA-wide in shared memory, stride <= 32 tail warp-local in registers
     const uint32_t half = P >> 1;
     for (uint32_t lk = 7; lk <= lp; lk++) {
         const uint32_t k = 1u << lk, hk = k >> 1;
@@ -160,7 +193,13 @@ __device__ void bitonic_sort_smem(uint64_t* a, uint32_t n) {
             }
             __syncthreads();
         }
-        for (uint32_t base = warp * 64; base < n; base += nwarps * 64) warp_half_cleaners(a, base, n, lane, 5);
+        for (uint32_t base = warp * 64; base < n; base += nwarps * 64) {
+            const uint32_t i0 = base + lane, i1 = base + lane + 32;
+            uint64_t r0 = i0 < n ? a[i0] : KEY_INF, r1 = i1 < n ? a[i1] : KEY_INF;
+            reg_half_cleaners(r0, r1, lane, 5);
+            if (i0 < n) a[i0] = r0;
+            if (i1 < n) a[i1] = r1;
+        }
         __syncthreads();
     }
 }
@@ -182,9 +221,7 @@ sort_pack_kernel(const uint32_t* __restrict__ tile_offset, uint64_t* __restrict_
     if (off + n > capacity) return;   // overflow is reported by the host wrapper (K > capacity)
     const uint64_t* sorted;
     if (n <= smem_keys) {
-        for (uint32_t j = threadIdx.x; j < n; j += SORT_THREADS) skeys[j] = keys[off + j];
-        __syncthreads();
-        if (n > 1) bitonic_sort_smem(skeys, n);
+        bitonic_sort_smem(skeys, n, keys + off);      // n == 1 included: phase 1 moves the key into shared memory
         sorted = skeys;
     } else {
         bitonic_sort_block(keys + off, n);

@@ -8,8 +8,9 @@ Mirrors the two calls the reference makes right after `render()`
 
     total, l1, ssim_value = photometric_loss(image, gt_image, mask, lambda_dssim)   # total == img + ssim terms
 
-The arithmetic is csrc/photometric.cu behind gg_photometric_forward / gg_photometric_backward.  Unlike the
-reference's ssim(), the rendered image and the ground truth are NOT multiplied by the mask in place.
+The arithmetic is csrc/photometric.cu behind gg_photometric_forward / gg_photometric_backward.  By default, unlike
+the reference's ssim(), the rendered image and the ground truth are NOT multiplied by the mask in place;
+`inplace_mask=True` reproduces that side effect (utils/loss_utils.py:44-46) for callers that rely on it.
 """
 
 from __future__ import annotations
@@ -90,7 +91,22 @@ class _Photometric(torch.autograd.Function):
 
 
 def photometric_loss(image: torch.Tensor, gt: torch.Tensor, mask: Optional[torch.Tensor] = None,
-                     lambda_dssim: float = 0.2):
+                     lambda_dssim: float = 0.2, inplace_mask: bool = False):
     """-> (total, l1, ssim): total = l1*(1-lambda) + 1 - ssim*lambda is differentiable w.r.t. `image`;
-    l1 and ssim are the detached components (the values of the reference's l1_loss / ssim)."""
-    return _Photometric.apply(image, gt, mask, float(lambda_dssim))
+    l1 and ssim are the detached components (the values of the reference's l1_loss / ssim).
+
+    inplace_mask=True follows the reference's call sequence to the letter: l1_loss on the unmasked tensors, then
+    ssim() multiplies `image` and `gt` by the mask IN PLACE (utils/loss_utils.py:44-46) -- both tensors hold the masked
+    values afterwards and the gradient flows through that in-place product (mask * mask for a soft mask's SSIM term,
+    exactly as in the reference)."""
+    lam = float(lambda_dssim)
+    if not inplace_mask or mask is None:
+        return _Photometric.apply(image, gt, mask, lam)
+    t_l1, l1, _ = _Photometric.apply(image, gt, mask, 0.0)               # l1 + 1, on the tensors as handed in
+    m = mask.to(image.dtype)
+    image.mul_(m)                                                        # autograd in-place op, as `img1 *= mask`
+    with torch.no_grad():
+        gt.mul_(m.to(gt.dtype))
+    t_ss, _, ssim_v = _Photometric.apply(image, gt, None, 1.0)           # 1 - ssim, on the masked tensors
+    total = (t_l1 - 1.0) * (1.0 - lam) + 1.0 - (1.0 - t_ss) * lam
+    return total, l1, ssim_v
