@@ -265,14 +265,26 @@ def main():
     # ---------------- CUDA graphs: the whole step (forward, fused L1, backward, exchange) as ONE launch --------------
     # The public API is called unchanged inside a torch.cuda.graph capture (rasterizer.py: the sync-free hinted forward
     # needs no host round trip; instance-capacity overflow is recorded on the device and checked after the loops).
-    # One graph per input slot (NS = 3): slot k owns a ground-truth buffer and a camera (view / projection / centre).
+    # One graph per input slot (NS = 2): slot k owns a ground-truth buffer and a camera (view / projection / centre,
+    # packed into one 35-float buffer so that a camera is ONE copy).
     import copy
     from gaussian_garments_b200 import rasterizer as _rast
-    NS = 3              # input slots: step i computes on slot i%NS while the host stages i+1 and reads back i-2
+    NS = 2              # input slots: step i computes on slot i%2 while step i+1's inputs land in the other one
     slot_gt = [torch.empty(3, H, W, device=dev) for _ in range(NS)]
     slot_u8 = [torch.zeros(3, H, W, dtype=torch.uint8, device=dev) for _ in range(NS)]     # e2e: the H2D payload
-    slot_cam = [[torch.empty(4, 4, device=dev), torch.empty(4, 4, device=dev), torch.empty(3, device=dev)] for _ in range(NS)]
+    slot_campack = [torch.empty(35, device=dev) for _ in range(NS)]
+    slot_cam = [[p_[0:16].view(4, 4), p_[16:32].view(4, 4), p_[32:35]] for p_ in slot_campack]
     slot_loss = [torch.zeros(1, device=dev) for _ in range(NS)]
+
+    def pack_cam(c):
+        return torch.cat([c.world_view_transform.reshape(-1), c.full_proj_transform.reshape(-1), c.camera_center.reshape(-1)])
+    cams_pack_dev = [pack_cam(c).contiguous() for c in cams]
+    # host side of the end-to-end loop: 8-bit frames and packed cameras in pinned memory, as a dataloader would hold them
+    gt_pinned = [u.pin_memory() for u in make_scene.gts_u8]
+    cam_pinned_pack = [pack_cam(c).contiguous().pin_memory() for c in cams_cpu]
+    cam_stage = [torch.zeros(35).pin_memory() for _ in range(NS)]     # the graph's H2D node reads these
+    loss_host = torch.zeros(NS).pin_memory()
+    copy_stream = torch.cuda.Stream(device=dev)
     slot_camobj = []
     for k in range(NS):
         c = copy.copy(cams[0])
@@ -281,8 +293,7 @@ def main():
     same_fov = all(abs(c.tanfovx - cams[0].tanfovx) < 1e-12 and abs(c.tanfovy - cams[0].tanfovy) < 1e-12 for c in cams)
 
     def load_slot(k, ci, gt=None):
-        for dst, src in zip(slot_cam[k], (cams[ci].world_view_transform, cams[ci].full_proj_transform, cams[ci].camera_center)):
-            dst.copy_(src, non_blocking=True)
+        slot_campack[k].copy_(cams_pack_dev[ci], non_blocking=True)
         if gt is not None:
             slot_gt[k].copy_(gt, non_blocking=True)
 
@@ -298,6 +309,19 @@ def main():
             if not around:
                 bucket.exchange_immediate()
         slot_loss[k].copy_(loss.detach().reshape(1))
+
+    def e2e_body(k):
+        """The end-to-end step as ONE graph: compute on slot k (8-bit GT read directly by the L1 kernels) while a forked
+        branch copies step i+1's inputs -- 8-bit frame and packed camera, from pinned host memory -- into slot 1-k; the
+        step's loss goes back to pinned host memory.  Slot 1-k is free: the step that used it ran earlier on this stream."""
+        cur = torch.cuda.current_stream()
+        copy_stream.wait_stream(cur)
+        with torch.cuda.stream(copy_stream):
+            slot_u8[1 - k].copy_(gt_pinned[1 - k], non_blocking=True)
+            slot_campack[1 - k].copy_(cam_stage[1 - k], non_blocking=True)
+        slot_body(k, True)
+        loss_host[k:k + 1].copy_(slot_loss[k], non_blocking=True)
+        cur.wait_stream(copy_stream)
 
     def exchanges_behind_graph():
         """'around' mode: both exchanges right behind the replayed step; the SH block runs on the side stream and the
@@ -337,11 +361,15 @@ def main():
                     _capi.launch_count(reset=True)
                     g_ = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g_):
-                        slot_body(k, from_u8)
+                        if from_u8:
+                            e2e_body(k)
+                        else:
+                            slot_body(k)
                     launches_per_replay = _capi.launch_count()
                     dst.append(g_)
             torch.cuda.synchronize()
-            graph_note = "whole step per launch; one graph per input slot (x2: device-resident float GT / 8-bit GT from the host)"
+            graph_note = ("whole step per launch; one graph per input slot (x2: device-resident float GT / end-to-end: "
+                          "compute + H2D prefetch of the next step's 8-bit GT and camera + D2H of the loss in one graph)")
             if world > 1:
                 graph_note += ("; exchanges issued eagerly behind each replay, device-side colour gate" if around
                                else "; exchanges captured inside the graph")
@@ -409,40 +437,38 @@ def main():
     value = world * args.steps / (total_ms * 1e-3)
 
     # ---------------- end-to-end through the public API with host buffers: `e2e` ----------------
-    gt_pinned = [u.pin_memory() for u in make_scene.gts_u8]        # 8-bit frames, as a dataloader would hold them
-    cam_pinned = [(c.world_view_transform.pin_memory(), c.full_proj_transform.pin_memory(), c.camera_center.pin_memory())
-                  for c in cams_cpu]
-    h2d = gt_pinned[0].numel() * 1 + (16 + 16 + 3) * 4
+    h2d = gt_pinned[0].numel() * 1 + 35 * 4
 
-    # The H2D copy of step i+1's inputs (pinned host -> the slot's device buffers) is issued on a copy stream while step
-    # i computes (what a pinned-memory DataLoader with non_blocking copies gives the reference); every copy still
-    # happens inside the timed region.  The loss of step i is copied D2H asynchronously and read on the host while step
-    # i+1 is already enqueued, so the GPU never waits for Python; every step's result is read inside the timed region.
-    copy_stream = torch.cuda.Stream(device=dev)
+    # Graph mode: every replay holds the step's compute AND, on a forked branch, the H2D copy of step i+1's inputs from
+    # pinned host memory (what a pinned-memory DataLoader with non_blocking copies gives the reference), plus the D2H
+    # copy of the step's loss.  The host stages the next camera into the pinned staging buffer, replays, and reads the
+    # loss of step i-2 -- every copy and every read happens inside the timed region.  Eager mode: the same pipeline with
+    # explicit streams / events.
     ready = [torch.cuda.Event() for _ in range(NS)]
-    loss_host = torch.zeros(NS).pin_memory()
     done = [torch.cuda.Event() for _ in range(NS)]
 
     def prefetch(i):
         ci = (i * world + rank) % N_CAMS
         with torch.cuda.stream(copy_stream):
             slot_u8[i % NS].copy_(gt_pinned[i % 2], non_blocking=True)
-            for dst, src in zip(slot_cam[i % NS], cam_pinned[ci]):
-                dst.copy_(src, non_blocking=True)
+            slot_campack[i % NS].copy_(cam_pinned_pack[ci], non_blocking=True)
             ready[i % NS].record(copy_stream)
 
     def e2e_run(n):
         vals = []
         cur = torch.cuda.current_stream()
-        prefetch(0)
-        for i in range(n):
-            k = i % NS
-            cur.wait_event(ready[k])
-            if i + 1 < n:
-                if i + 1 >= NS:
-                    copy_stream.wait_event(done[(i + 1 - NS) % NS])    # slot (i+1)%NS is free once step i+1-NS has finished
-                prefetch(i + 1)
-            if graphs is not None:
+        if graphs is not None:
+            cam_stage[0].copy_(cam_pinned_pack[rank % N_CAMS])
+            slot_u8[0].copy_(gt_pinned[0], non_blocking=True)              # step 0's inputs (later ones: inside the graphs)
+            slot_campack[0].copy_(cam_stage[0], non_blocking=True)
+            for i in range(n):
+                k = i % 2
+                if i >= 2:                                                  # read step i-2's loss: two steps stay queued
+                    tw = time.perf_counter()
+                    done[k].synchronize()
+                    e2e_run.wait_s += time.perf_counter() - tw
+                    vals.append(float(loss_host[k]))
+                cam_stage[1 - k].copy_(cam_pinned_pack[((i + 1) * world + rank) % N_CAMS])   # next camera -> staging
                 graphs_u8[k].replay()
                 if around:
                     exchanges_behind_graph()
@@ -451,14 +477,28 @@ def main():
                 elif i == n - 1 and world > 1:
                     bucket.exchange_deferred_async()
                     bucket.wait()
-                loss = slot_loss[k]
-            else:
-                loss = step(i, slot_u8[k], slot_camobj[k], drain=(i == n - 1))
+                done[k].record(cur)
+            for j in range(max(0, n - 2), n):
+                done[j % 2].synchronize()
+                vals.append(float(loss_host[j % 2]))
+            assert len(vals) == n and all(math.isfinite(v) for v in vals)
+            return vals
+        prefetch(0)
+        for i in range(n):
+            k = i % NS
+            cur.wait_event(ready[k])
+            if i + 1 < n:
+                if i + 1 >= NS:
+                    copy_stream.wait_event(done[(i + 1 - NS) % NS])    # slot (i+1)%NS is free once step i+1-NS has finished
+                prefetch(i + 1)
+            loss = step(i, slot_u8[k], slot_camobj[k], drain=(i == n - 1))
             loss_host[k:k + 1].copy_(loss.detach().reshape(1), non_blocking=True)   # D2H read of the result
             done[k].record(cur)
-            if i >= NS - 1:                                        # read step i-2's loss: two steps stay queued on the GPU
+            if i >= NS - 1:
                 j = i - (NS - 1)
+                tw = time.perf_counter()
                 done[j % NS].synchronize()
+                e2e_run.wait_s += time.perf_counter() - tw
                 vals.append(float(loss_host[j % NS]))
         for j in range(max(0, n - (NS - 1)), n):
             done[j % NS].synchronize()
@@ -476,11 +516,13 @@ def main():
         hb1.record(copy_stream)
     torch.cuda.synchronize()
     h2d_gbs = 4 * gt_pinned[0].numel() / (hb0.elapsed_time(hb1) * 1e-3) / 1e9
+    e2e_run.wait_s = 0.0
     e2e_run(3)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     e_steps = max(10, args.steps // 2)
+    e2e_run.wait_s = 0.0
     t0 = time.perf_counter()
     e2e_vals = e2e_run(e_steps)
     torch.cuda.synchronize()
@@ -625,6 +667,9 @@ def main():
                             "exchange": (("around" if around else "ingraph") if world > 1 and graphs is not None else None),
                             "colour_gate_timed_out": gate_timed_out},
             "e2e_loss_first_last": [e2e_vals[0], e2e_vals[-1]],
+            "e2e_host": {"blocked_on_gpu_ms_per_step": round(1e3 * e2e_run.wait_s / e_steps, 4),
+                         "wall_ms_per_step": round(1e3 * e_dt / e_steps, 4),
+                         "note": "blocked ~ 0 means the host loop, not the GPU, paces the end-to-end number"},
             "with_ssim_loss": ssim_line,
             "forward_stats": dict(_rasterizer_stats()),
             "clocks": clocks, "gpu_launches": int(launches),
@@ -632,7 +677,7 @@ def main():
                     "what": "pinned-host 8-bit GT frame + camera matrices copied H2D every step (copy stream, overlapping the "
                             "previous step's compute), dequantised inside the fused L1 kernels, public GaussianRasterizer API fwd + fused "
                             "L1 + bwd (CUDA-graph replay of that call sequence unless --eager), every step's loss copied D2H "
-                            "(async, read two steps later: three input slots); wall clock, max over ranks",
+                            "(async, read two steps later); in graph mode copies and compute of a step are one graph launch; wall clock, max over ranks",
                     "steps": e_steps, "h2d_gbs_measured": h2d_gbs},
             "roofline": roofline}
     if collective is not None:

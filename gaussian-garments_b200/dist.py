@@ -92,6 +92,11 @@ class GradBucket:
         pad_words = int(hdl.signal_pad_size) // 4
         blocks = max(2, min(72, pad_words // self.world))      # one pad word per (block, peer)
         self._blocks = (max(1, blocks // 3), max(1, blocks - blocks // 3))      # (immediate, deferred)
+        env = os.environ.get("GG_AR_BLOCKS")                   # "a,b": experiment knob, a + b <= pad_words // world
+        if env:
+            a, b = (int(x) for x in env.split(","))
+            if a >= 1 and b >= 1 and (a + b) * self.world <= pad_words and max(a, b) <= 148:
+                self._blocks = (a, b)
         self._slot0 = (0, self._blocks[0] * self.world)
         self.flat = flat
         self.impl = "nvls_multimem"

@@ -102,7 +102,8 @@ def photometric_loss(image: torch.Tensor, gt: torch.Tensor, mask: Optional[torch
     lam = float(lambda_dssim)
     if not inplace_mask or mask is None:
         return _Photometric.apply(image, gt, mask, lam)
-    t_l1, l1, _ = _Photometric.apply(image, gt, mask, 0.0)               # l1 + 1, on the tensors as handed in
+    # l1 + 1 on the tensors as handed in; the op keeps copies for its backward because both are overwritten below
+    t_l1, l1, _ = _Photometric.apply(image.clone(), gt.clone(), mask, 0.0)
     m = mask.to(image.dtype)
     image.mul_(m)                                                        # autograd in-place op, as `img1 *= mask`
     with torch.no_grad():
