@@ -326,8 +326,12 @@ def main():
     def exchanges_behind_graph():
         """'around' mode: both exchanges right behind the replayed step; the SH block runs on the side stream and the
         NEXT replay's colour stage waits for it on the device (dist.GradBucket.use_device_gate)."""
-        bucket.exchange_immediate()
-        bucket.exchange_deferred_async()
+        if os.environ.get("GG_BENCH_SH_FIRST") == "1":     # experiment: both exchanges in flight at once
+            bucket.exchange_deferred_async()
+            bucket.exchange_immediate()
+            return
+        bucket.exchange_immediate()                        # geometry first: it is on the critical path
+        bucket.exchange_deferred_async()                   # SH behind it, under the next projection / binning
 
     graphs, graph_note, launches_per_replay = None, None, 0
     around = False
