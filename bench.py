@@ -154,6 +154,29 @@ def algorithmic_bytes(N, K, P, T, M=16):
     }
 
 
+def bind_to_gpu_numa_node(local):
+    """Host plumbing for the end-to-end loop: run this rank's host thread on the CPU cores of the NUMA node its GPU hangs
+    off, BEFORE the pinned staging buffers are allocated (first touch puts them in that node's DRAM), so that the per-step
+    H2D copies of the 8 ranks do not all cross the socket interconnect.  Returns a short description (or why not)."""
+    try:
+        p = torch.cuda.get_device_properties(local)
+        bdf = f"{getattr(p, 'pci_domain_id', 0):04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        if node < 0:
+            return f"{bdf}: no NUMA affinity reported"
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return f"{bdf}: node {node} has no usable cores"
+        os.sched_setaffinity(0, cpus)
+        return f"{bdf}: NUMA node {node}, {len(cpus)} cores"
+    except Exception as e:
+        return f"not bound ({type(e).__name__}: {str(e)[:80]})"
+
+
 def make_scene(args, dev):
     import diff_gaussian_rasterization_depth_alpha  # noqa: F401 (registers gaussian_garments_b200)
     import gaussian_garments_b200 as gg
@@ -225,6 +248,7 @@ def main():
     import torch.distributed as dist
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_note = bind_to_gpu_numa_node(local) if os.environ.get("GG_BENCH_NUMA", "1") == "1" else "off (GG_BENCH_NUMA=0)"
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -520,6 +544,11 @@ def main():
         hb1.record(copy_stream)
     torch.cuda.synchronize()
     h2d_gbs = 4 * gt_pinned[0].numel() / (hb0.elapsed_time(hb1) * 1e-3) / 1e9
+    h2d_gbs_min = h2d_gbs
+    if world > 1:                                          # all ranks copy at the same time: the slowest link paces e2e
+        tmin = torch.tensor([h2d_gbs], dtype=torch.float64, device=dev)
+        dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+        h2d_gbs_min = float(tmin.item())
     e2e_run.wait_s = 0.0
     e2e_run(3)
     torch.cuda.synchronize()
@@ -682,7 +711,8 @@ def main():
                             "previous step's compute), dequantised inside the fused L1 kernels, public GaussianRasterizer API fwd + fused "
                             "L1 + bwd (CUDA-graph replay of that call sequence unless --eager), every step's loss copied D2H "
                             "(async, read two steps later); in graph mode copies and compute of a step are one graph launch; wall clock, max over ranks",
-                    "steps": e_steps, "h2d_gbs_measured": h2d_gbs},
+                    "steps": e_steps, "h2d_gbs_measured": h2d_gbs, "h2d_gbs_min_over_ranks": h2d_gbs_min,
+                    "host_numa_binding": numa_note},
             "roofline": roofline}
     if collective is not None:
         line["collective"] = collective

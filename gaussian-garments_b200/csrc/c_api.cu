@@ -4,8 +4,10 @@
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
+#include <map>
 #include <mutex>
 #include <cstring>
+#include <utility>
 #include "common.cuh"
 
 namespace {
@@ -63,6 +65,51 @@ int cuda_fail(cudaError_t e, const char* where) {
         cudaError_t _e = (call);                              \
         if (_e != cudaSuccess) return cuda_fail(_e, #call);   \
     } while (0)
+
+// ---- forward fork: SH -> RGB on a side stream, concurrently with the tile scan and the instance emission ----------
+// sh_color is HBM-bound and needs only the projection's radii; tile_scan is ONE CTA and emit is atomics-bound, so the
+// three overlap almost for free.  One fork set per (device, caller stream): gg_forward_project records `projected`
+// right behind project_kernel, gg_forward_color launches on `side` behind it and records `colored`, gg_forward_render
+// joins before the first reader of the colours.  Event record / wait pairs are capturable, so the fork survives inside
+// a CUDA graph.  Side streams come from a small per-device pool created on first (eager) use -- nothing is created
+// while a capture is in progress except events.
+struct ForkSet {
+    cudaStream_t side = nullptr;
+    cudaEvent_t projected = nullptr, colored = nullptr;
+    bool armed = false;        // `projected` was recorded by the latest gg_forward_project on this stream
+    bool pending = false;      // sh_color is in flight on `side`: the next render on this stream must join
+};
+constexpr int FORK_POOL = 4, FORK_MAX_DEV = 64;
+std::mutex g_fork_mu;
+std::map<std::pair<int, cudaStream_t>, ForkSet> g_forks;
+cudaStream_t g_fork_pool[FORK_MAX_DEV][FORK_POOL];
+bool g_fork_pool_made[FORK_MAX_DEV] = {false};
+int g_fork_next[FORK_MAX_DEV] = {0};
+
+// nullptr when forking is off (GG_FWD_FORK=0, per-kernel timing on, debug mode) or the pool cannot be set up here
+ForkSet* fork_set(int device, cudaStream_t s, bool debug) {
+    static const bool off = []() { const char* e = getenv("GG_FWD_FORK"); return e && !strcmp(e, "0"); }();
+    if (off || debug || g_timing.load() != 0 || device < 0 || device >= FORK_MAX_DEV) return nullptr;
+    std::lock_guard<std::mutex> lk(g_fork_mu);
+    if (!g_fork_pool_made[device]) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(s, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return nullptr;
+        for (int i = 0; i < FORK_POOL; i++)
+            if (cudaStreamCreateWithFlags(&g_fork_pool[device][i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        g_fork_pool_made[device] = true;
+    }
+    auto key = std::make_pair(device, s);
+    auto it = g_forks.find(key);
+    if (it == g_forks.end()) {
+        ForkSet f;
+        f.side = g_fork_pool[device][g_fork_next[device]++ % FORK_POOL];
+        if (cudaEventCreateWithFlags(&f.projected, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&f.colored, cudaEventDisableTiming) != cudaSuccess)
+            return nullptr;
+        it = g_forks.emplace(key, f).first;
+    }
+    return &it->second;
+}
 
 // environment switches are read ONCE per process (function-local statics at the call sites)
 inline bool env_is(const char* name, const char* value) {
@@ -203,6 +250,10 @@ int gg_forward_project(const gg_view* view, const gg_inputs* in, void* geom_ws, 
     GG_CUDA(cudaMemsetAsync(t.count, 0, (size_t)((char*)t.offset - (char*)t.count), s));
     { ScopedKernelTimer kt(K_PROJECT, s); g_launches += launch_project(*view, *in, g, t, radii, s); }
     GG_AFTER("project_kernel");
+    if (ForkSet* f = fork_set(device, s, view->debug != 0)) {      // fork point for the colour kernel (see ForkSet)
+        GG_CUDA(cudaEventRecord(f->projected, s));
+        f->armed = true;
+    }
     { ScopedKernelTimer kt(K_SCAN, s); g_launches += launch_tile_scan(T, t, s); }
     GG_AFTER("tile_scan_kernel");
     if (num_rendered_host) GG_CUDA(cudaMemcpyAsync(num_rendered_host, t.misc, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
@@ -219,6 +270,16 @@ int gg_forward_color(const gg_view* view, const gg_inputs* in, void* geom_ws, co
     cudaStream_t s = (cudaStream_t)stream;
     GeomWS g;
     geom_layout(geom_ws, view->num_gaussians, &g);
+    ForkSet* f = fork_set(device, s, view->debug != 0);
+    if (f && f->armed) {            // side stream, behind the projection only; joined by the next render on `s`
+        f->armed = false;
+        GG_CUDA(cudaStreamWaitEvent(f->side, f->projected, 0));
+        g_launches += launch_sh_color(*view, *in, g, radii, f->side);
+        GG_CUDA(cudaGetLastError());
+        GG_CUDA(cudaEventRecord(f->colored, f->side));
+        f->pending = true;
+        return 0;
+    }
     { ScopedKernelTimer kt(K_SHCOLOR, s); g_launches += launch_sh_color(*view, *in, g, radii, s); }
     GG_AFTER("sh_color_kernel");
     return 0;
@@ -257,6 +318,16 @@ static int forward_render_impl(const gg_view* view, const gg_inputs* in, const v
     GG_CUDA(cudaMemsetAsync(t.fill, 0, (size_t)T * sizeof(uint32_t), s));
     { ScopedKernelTimer kt(K_EMIT, s); g_launches += launch_emit(*view, g, t, radii, (uint64_t*)key_ws, cap, s); }
     GG_AFTER("emit_kernel");
+    {   // join a colour kernel forked by gg_forward_color: sort_pack / the lazy kernel read geom.rgb
+        std::unique_lock<std::mutex> lk(g_fork_mu);
+        auto it = g_forks.find(std::make_pair(device, s));
+        if (it != g_forks.end() && it->second.pending) {
+            it->second.pending = false;
+            cudaEvent_t ev = it->second.colored;
+            lk.unlock();
+            GG_CUDA(cudaStreamWaitEvent(s, ev, 0));
+        }
+    }
     // Forward path: "tma" = per-tile full sort + pack, then the bulk-TMA streamed blend;
     //               "lazy" = fused bucket-sort + pack + blend that stops at tile saturation (dense scenes).
     // auto: lazy when some tile holds more instances than the default shared-memory sort handles.

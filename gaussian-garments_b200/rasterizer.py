@@ -245,6 +245,13 @@ class _RasterizeGaussians(torch.autograd.Function):
                     word = _pinned_word(di)
                     if not capturing:
                         _graph_flag(dev)         # the sticky overflow words must exist before any capture starts
+                    hkey = (di, N, W, H)
+                    hint = None if s.debug else _hints.get(hkey)
+                    gate = COLOR_GATE.get(di)
+                    if gate is not None and hint is None and not isinstance(gate, DeviceGate):
+                        # unhinted call (first of its shape): no late-colour order; the colour kernel may be forked onto
+                        # the library's side stream right behind the projection, so the whole forward waits here
+                        stream.wait_event(gate)
                     _capi.check(lib.gg_forward_project(C.byref(view), C.byref(inputs), geom_ws.data_ptr(),
                                                        tile_ws.data_ptr(), radii.data_ptr(),
                                                        None if capturing else word.data_ptr(), di, sp),
@@ -252,9 +259,6 @@ class _RasterizeGaussians(torch.autograd.Function):
                     if not capturing:
                         k_ready = torch.cuda.Event()
                         k_ready.record(stream)
-                    hkey = (di, N, W, H)
-                    hint = None if s.debug else _hints.get(hkey)
-                    gate = COLOR_GATE.get(di)
                     # A pending SH-gradient exchange (dist.GradBucket) gates only the colour stage.  With a capacity
                     # hint the colour stage moves BEHIND emission and sorting (late-colour call), so the exchange
                     # overlaps with projection + emit + sort; without a hint it simply waits here.
@@ -264,8 +268,6 @@ class _RasterizeGaussians(torch.autograd.Function):
                         raise RuntimeError("gaussian-garments_b200: a device colour gate needs the hinted (late-colour) "
                                            "forward: run one eager forward of this shape first")
                     if not late["on"]:
-                        if gate is not None:
-                            stream.wait_event(gate)
                         _capi.check(lib.gg_forward_color(C.byref(view), C.byref(inputs), geom_ws.data_ptr(),
                                                          radii.data_ptr(), di, sp), "gg_forward_color")
                     if capturing:

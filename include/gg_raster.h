@@ -95,7 +95,12 @@ int gg_forward_project(const gg_view* view, const gg_inputs* in, void* geom_ws, 
 
 /* ---- forward, stage 1b: the colour part of preprocessCUDA (SH deg<=3 -> RGB, +0.5, clamp;
  * or a copy of colors_precomp).  Enqueued behind the K read-back so that the host's wait
- * for K overlaps this kernel (the 57.6 MB SH read at 300k Gaussians).                     */
+ * for K overlaps this kernel (the 57.6 MB SH read at 300k Gaussians).
+ * When the preceding gg_forward_project ran on the same (device, stream) the kernel is launched on a library-owned
+ * side stream, ordered behind the projection only, so that it runs CONCURRENTLY with the tile scan and the instance
+ * emission; the next gg_forward_render on `stream` joins it before the first reader of the colours.  The caller sees
+ * plain stream semantics on `stream` (capturable in a CUDA graph).  GG_FWD_FORK=0, debug views and per-kernel timing
+ * keep everything on `stream`.                                                                                    */
 int gg_forward_color(const gg_view* view, const gg_inputs* in, void* geom_ws, const int32_t* radii,
                      int device, void* stream);
 
