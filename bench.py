@@ -293,7 +293,9 @@ def main():
     # packed into one 35-float buffer so that a camera is ONE copy).
     import copy
     from gaussian_garments_b200 import rasterizer as _rast
-    NS = 2              # input slots: step i computes on slot i%2 while step i+1's inputs land in the other one
+    NS = 4              # input slots (even): step i computes on slot i%NS while step i+1's inputs land in the next one;
+                        # the end-to-end loop reads the loss of step i-(NS-1), so NS-1 steps stay queued on the GPU and a
+                        # descheduled host thread on ONE rank does not stall every rank at the next exchange barrier
     slot_gt = [torch.empty(3, H, W, device=dev) for _ in range(NS)]
     slot_u8 = [torch.zeros(3, H, W, dtype=torch.uint8, device=dev) for _ in range(NS)]     # e2e: the H2D payload
     slot_campack = [torch.empty(35, device=dev) for _ in range(NS)]
@@ -336,13 +338,14 @@ def main():
 
     def e2e_body(k):
         """The end-to-end step as ONE graph: compute on slot k (8-bit GT read directly by the L1 kernels) while a forked
-        branch copies step i+1's inputs -- 8-bit frame and packed camera, from pinned host memory -- into slot 1-k; the
-        step's loss goes back to pinned host memory.  Slot 1-k is free: the step that used it ran earlier on this stream."""
+        branch copies step i+1's inputs -- 8-bit frame and packed camera, from pinned host memory -- into slot k+1; the
+        step's loss goes back to pinned host memory.  Slot k+1 is free: the step that used it ran earlier on this stream."""
         cur = torch.cuda.current_stream()
         copy_stream.wait_stream(cur)
         with torch.cuda.stream(copy_stream):
-            slot_u8[1 - k].copy_(gt_pinned[1 - k], non_blocking=True)
-            slot_campack[1 - k].copy_(cam_stage[1 - k], non_blocking=True)
+            kn = (k + 1) % NS
+            slot_u8[kn].copy_(gt_pinned[kn % 2], non_blocking=True)
+            slot_campack[kn].copy_(cam_stage[kn], non_blocking=True)
         slot_body(k, True)
         loss_host[k:k + 1].copy_(slot_loss[k], non_blocking=True)
         cur.wait_stream(copy_stream)
@@ -489,14 +492,17 @@ def main():
             cam_stage[0].copy_(cam_pinned_pack[rank % N_CAMS])
             slot_u8[0].copy_(gt_pinned[0], non_blocking=True)              # step 0's inputs (later ones: inside the graphs)
             slot_campack[0].copy_(cam_stage[0], non_blocking=True)
+            L = NS - 1
             for i in range(n):
-                k = i % 2
-                if i >= 2:                                                  # read step i-2's loss: two steps stay queued
+                k = i % NS
+                if i >= L:                                                  # read step i-L's loss: L steps stay queued
+                    j = (i - L) % NS
                     tw = time.perf_counter()
-                    done[k].synchronize()
+                    done[j].synchronize()
                     e2e_run.wait_s += time.perf_counter() - tw
-                    vals.append(float(loss_host[k]))
-                cam_stage[1 - k].copy_(cam_pinned_pack[((i + 1) * world + rank) % N_CAMS])   # next camera -> staging
+                    vals.append(float(loss_host[j]))
+                # next camera -> staging buffer k+1 (its previous reader, replay i-L, has completed: synchronised above)
+                cam_stage[(k + 1) % NS].copy_(cam_pinned_pack[((i + 1) * world + rank) % N_CAMS])
                 graphs_u8[k].replay()
                 if around:
                     exchanges_behind_graph()
@@ -506,9 +512,9 @@ def main():
                     bucket.exchange_deferred_async()
                     bucket.wait()
                 done[k].record(cur)
-            for j in range(max(0, n - 2), n):
-                done[j % 2].synchronize()
-                vals.append(float(loss_host[j % 2]))
+            for j in range(max(0, n - L), n):
+                done[j % NS].synchronize()
+                vals.append(float(loss_host[j % NS]))
             assert len(vals) == n and all(math.isfinite(v) for v in vals)
             return vals
         prefetch(0)
@@ -710,7 +716,7 @@ def main():
                     "what": "pinned-host 8-bit GT frame + camera matrices copied H2D every step (copy stream, overlapping the "
                             "previous step's compute), dequantised inside the fused L1 kernels, public GaussianRasterizer API fwd + fused "
                             "L1 + bwd (CUDA-graph replay of that call sequence unless --eager), every step's loss copied D2H "
-                            "(async, read two steps later); in graph mode copies and compute of a step are one graph launch; wall clock, max over ranks",
+                            "(async, read three steps later); in graph mode copies and compute of a step are one graph launch; wall clock, max over ranks",
                     "steps": e_steps, "h2d_gbs_measured": h2d_gbs, "h2d_gbs_min_over_ranks": h2d_gbs_min,
                     "host_numa_binding": numa_note},
             "roofline": roofline}

@@ -274,7 +274,9 @@ int gg_forward_color(const gg_view* view, const gg_inputs* in, void* geom_ws, co
     if (f && f->armed) {            // side stream, behind the projection only; joined by the next render on `s`
         f->armed = false;
         GG_CUDA(cudaStreamWaitEvent(f->side, f->projected, 0));
-        g_launches += launch_sh_color(*view, *in, g, radii, f->side);
+        // a resident-size grid (default 4 CTAs per SM on 148 SMs) that strides over the slabs: see sh_color16_kernel
+        static const int fork_blocks = []() { const char* e = getenv("GG_SH_FORK_BLOCKS"); return e ? atoi(e) : 592; }();
+        g_launches += launch_sh_color(*view, *in, g, radii, f->side, fork_blocks);
         GG_CUDA(cudaGetLastError());
         GG_CUDA(cudaEventRecord(f->colored, f->side));
         f->pending = true;

@@ -134,7 +134,8 @@ inline size_t accum_layout(void* base, int64_t N, AccumWS* ws) {
 int launch_project(const gg_view& v, const gg_inputs& in, const GeomWS& g, const TileWS& t, int32_t* radii,
                    cudaStream_t s);
 int launch_tile_scan(int T, const TileWS& t, cudaStream_t s);
-int launch_sh_color(const gg_view& v, const gg_inputs& in, const GeomWS& g, const int32_t* radii, cudaStream_t s);
+int launch_sh_color(const gg_view& v, const gg_inputs& in, const GeomWS& g, const int32_t* radii, cudaStream_t s,
+                    int max_blocks = 0);
 int launch_emit(const gg_view& v, const GeomWS& g, const TileWS& t, const int32_t* radii, uint64_t* keys,
                 uint32_t capacity, cudaStream_t s);
 int launch_color_fill(const gg_view& v, const GeomWS& g, const TileWS& t, const RecordWS& r, uint32_t capacity, cudaStream_t s);

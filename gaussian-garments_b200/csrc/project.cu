@@ -273,50 +273,55 @@ __device__ __forceinline__ void sh_to_rgb(int deg, const float* sh /*[M*3]*/, fl
     rgb[2] = fmaxf(r2 + 0.5f, 0.f);
 }
 
+// Slab loop: with a full grid (one slab per CTA) the loop runs once; the forked launch (c_api.cu: ForkSet) uses a SMALL
+// resident grid striding over the slabs, so that the kernel never queues more CTAs than fit -- the block scheduler
+// hands out CTAs in launch order, and a full grid of 2 344 pending CTAs would keep the concurrently running
+// emit_kernel's CTAs waiting until the colour kernel has been issued completely.
 __global__ void __launch_bounds__(SH_BLOCK)
 sh_color16_kernel(int N, int deg, const float* __restrict__ means3D, const float* __restrict__ shs,
                   const float* __restrict__ campos, const int32_t* __restrict__ radii, float* __restrict__ rgb_out) {
     __shared__ __align__(16) float4 rows[SH_BLOCK * SH_ROW_U];
-    const int base = blockIdx.x * SH_BLOCK;
-    const int i = base + threadIdx.x;
-    const int nG = min(SH_BLOCK, N - base);
-    const bool live = (i < N) && (radii[i] > 0);
-    if (!__syncthreads_or(live)) return;   // whole slab culled: skip its 24 KB read
-    const float4* src = reinterpret_cast<const float4*>(shs) + (size_t)base * 12;
-    for (int u = threadIdx.x; u < nG * 12; u += SH_BLOCK) {
-        const int gI = u / 12, j = u - gI * 12;
-        cp_async16(&rows[gI * SH_ROW_U + j], src + u);
-    }
-    cp_async_wait_all();
-    __syncthreads();
-    if (!live) return;
-    float dx = means3D[3 * (size_t)i] - campos[0], dy = means3D[3 * (size_t)i + 1] - campos[1],
-          dz = means3D[3 * (size_t)i + 2] - campos[2];
-    const float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
-    float b[16];
-#pragma unroll
-    for (int k = 0; k < 16; k++) b[k] = 0.f;              // coefficients above the active degree contribute nothing
-    sh_basis(deg, dx * inv, dy * inv, dz * inv, b);
-    const int nb = (deg + 1) * (deg + 1);
-    // accumulate straight out of the padded row (the 48 coefficients never sit in registers together: 72 -> ~40 regs)
-    float acc[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-    for (int j = 0; j < 12; j++) {
-        const float4 q = rows[threadIdx.x * SH_ROW_U + j];
-        const float v[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-        for (int e = 0; e < 4; e++) {
-            const int f = 4 * j + e;                          // flat index = 3 k + channel (compile-time)
-            if (f / 3 < nb) acc[f % 3] += b[f / 3] * v[e];    // coefficients above the active degree are ignored
+    const int nslabs = (N + SH_BLOCK - 1) / SH_BLOCK;
+    const float cx = campos[0], cy = campos[1], cz = campos[2];
+    for (int slab = blockIdx.x; slab < nslabs; slab += gridDim.x) {
+        const int base = slab * SH_BLOCK;
+        const int i = base + threadIdx.x;
+        const int nG = min(SH_BLOCK, N - base);
+        const bool live = (i < N) && (radii[i] > 0);
+        if (!__syncthreads_or(live)) continue;   // whole slab culled: skip its 24 KB read
+        const float4* src = reinterpret_cast<const float4*>(shs) + (size_t)base * 12;
+        for (int u = threadIdx.x; u < nG * 12; u += SH_BLOCK) {
+            const int gI = u / 12, j = u - gI * 12;
+            cp_async16(&rows[gI * SH_ROW_U + j], src + u);
         }
+        cp_async_wait_all();
+        __syncthreads();
+        if (live) {
+            float dx = means3D[3 * (size_t)i] - cx, dy = means3D[3 * (size_t)i + 1] - cy, dz = means3D[3 * (size_t)i + 2] - cz;
+            const float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
+            float b[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) b[k] = 0.f;          // coefficients above the active degree contribute nothing
+            sh_basis(deg, dx * inv, dy * inv, dz * inv, b);
+            const int nb = (deg + 1) * (deg + 1);
+            // accumulate straight out of the padded row (the 48 coefficients never sit in registers together)
+            float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+            for (int j = 0; j < 12; j++) {
+                const float4 q = rows[threadIdx.x * SH_ROW_U + j];
+                const float v[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    const int f = 4 * j + e;                          // flat index = 3 k + channel (compile-time)
+                    if (f / 3 < nb) acc[f % 3] += b[f / 3] * v[e];    // coefficients above the active degree are ignored
+                }
+            }
+            rgb_out[3 * (size_t)i] = fmaxf(acc[0] + 0.5f, 0.f);
+            rgb_out[3 * (size_t)i + 1] = fmaxf(acc[1] + 0.5f, 0.f);
+            rgb_out[3 * (size_t)i + 2] = fmaxf(acc[2] + 0.5f, 0.f);
+        }
+        __syncthreads();                         // the rows are overwritten by the next slab
     }
-    float rgb[3];
-    rgb[0] = fmaxf(acc[0] + 0.5f, 0.f);
-    rgb[1] = fmaxf(acc[1] + 0.5f, 0.f);
-    rgb[2] = fmaxf(acc[2] + 0.5f, 0.f);
-    rgb_out[3 * (size_t)i] = rgb[0];
-    rgb_out[3 * (size_t)i + 1] = rgb[1];
-    rgb_out[3 * (size_t)i + 2] = rgb[2];
 }
 
 // generic M (1, 4, 9, ...) or precomputed colours: direct loads
@@ -372,12 +377,14 @@ int launch_tile_scan(int T, const TileWS& t, cudaStream_t s) {
     return 1;
 }
 
-int launch_sh_color(const gg_view& v, const gg_inputs& in, const GeomWS& g, const int32_t* radii, cudaStream_t s) {
+int launch_sh_color(const gg_view& v, const gg_inputs& in, const GeomWS& g, const int32_t* radii, cudaStream_t s,
+                    int max_blocks) {
     const int N = v.num_gaussians;
     if (N == 0) return 0;
     if (!in.colors_precomp && v.sh_coeffs == 16) {
-        sh_color16_kernel<<<(N + SH_BLOCK - 1) / SH_BLOCK, SH_BLOCK, 0, s>>>(N, v.sh_degree, in.means3D, in.shs,
-                                                                             in.campos, radii, g.rgb);
+        int blocks = (N + SH_BLOCK - 1) / SH_BLOCK;
+        if (max_blocks > 0 && blocks > max_blocks) blocks = max_blocks;
+        sh_color16_kernel<<<blocks, SH_BLOCK, 0, s>>>(N, v.sh_degree, in.means3D, in.shs, in.campos, radii, g.rgb);
     } else {
         sh_color_generic_kernel<<<(N + 255) / 256, 256, 0, s>>>(N, v.sh_coeffs, v.sh_degree, in.means3D, in.shs,
                                                                 in.colors_precomp, in.campos, radii, g.rgb);
