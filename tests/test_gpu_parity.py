@@ -1114,6 +1114,44 @@ def test_photometric_l1_with_8bit_ground_truth_equals_float_path():
 
 
 # ------------------------------------------------------------------------------------ BASELINE-size cfg4 / cfg5 parity
+_V1_CHILD = r"""
+import sys, torch
+sys.path.insert(0, {root!r}); sys.path.insert(0, {tests!r})
+import helpers as h
+import gaussian_garments_b200 as gg
+st = gg.scenes.random_cloud(6000, seed=23)
+cam = gg.scenes.cfg1_camera(352, 240)
+g = torch.Generator().manual_seed(5)
+grads = (torch.randn(3, 240, 352, generator=g), torch.randn(1, 240, 352, generator=g), torch.randn(1, 240, 352, generator=g))
+out = h.run_cuda(h.settings_for(cam, st, device=torch.device("cuda:0")), st, grads)
+torch.save(out, {dst!r})
+"""
+
+
+def test_decoupled_warp_blend_kernels_equal_the_barrier_synchronised_ones(tmp_path):
+    """The v2 blend kernels recycle their TMA stages through mbarriers (no __syncthreads); compute-sanitizer's racecheck
+    does not model that hand-off and flags it.  The round-1 kernels (GG_FWD_KERNEL=v1 / GG_BWD_PATH=v1, CTA-barrier
+    recycling, racecheck-clean) run in a child process on the same seeded scene: the forward images must agree to the
+    last bits (same per-pixel accumulation order), the gradients up to the float-atomic summation order."""
+    import subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = {}
+    for tag, env in (("v2", {}), ("v1", {"GG_FWD_KERNEL": "v1", "GG_BWD_PATH": "v1"})):
+        dst = str(tmp_path / f"{tag}.pt")
+        code = _V1_CHILD.format(root=root, tests=os.path.join(root, "tests"), dst=dst)
+        e = dict(os.environ, **env)
+        r = subprocess.run([sys.executable, "-c", code], env=e, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs[tag] = torch.load(dst)
+    a, b = outs["v2"], outs["v1"]
+    assert torch.equal(a["radii"], b["radii"])
+    for k in ("color", "depth", "alpha"):          # same per-pixel accumulation order; FMA contraction may differ
+        assert float((a[k] - b[k]).abs().max()) <= 2e-6 * max(1.0, float(b[k].abs().max())), k
+    for k, ga in a["grads"].items():
+        if ga is not None:
+            assert h.rel_inf(ga, b["grads"][k]) <= 2e-5, k
+
+
 def test_cfg4_full_size_mixed_resolution_with_mesh_vertex_gradient():
     """BASELINE configs[3] at full size: 150k mesh-bound Gaussians (25k faces x 6), SH degree 0 with an [N,1,3] tensor
     (s2_registration.py:158), one 1280x720 and one 1920x1080 camera of the 32-camera ring, gradients chained to mesh.v
