@@ -73,8 +73,10 @@ blend_fwd2_kernel(const uint32_t* __restrict__ tile_offset, const float4* __rest
     __syncthreads();
 
     float T = 1.f, C0 = 0.f, C1 = 0.f, C2 = 0.f, Dp = 0.f, Ac = 0.f;
+    // Tm = the transmittance while the pixel is live, 0 once it has stopped (or lies outside the image): a stopped pixel
+    // then fails the T_STOP test by itself (0 * (1 - alpha) < T_STOP) -- no separate flag to carry through the loop
+    float Tm = inside ? 1.f : 0.f;
     uint32_t last = 0;
-    bool done = !inside;
     bool warp_done = false;               // all 32 pixels of this warp are saturated (or outside the image)
     int issued = 0;                       // thread 0 only
     int q = 0;
@@ -147,26 +149,25 @@ blend_fwd2_kernel(const uint32_t* __restrict__ tile_offset, const float4* __rest
                     const float dx = a.x - fx, dy = a.y - fy;
                     const float e2 = dx * (a.z * dx + a.w * dy) + (c.x * dy) * dy;     // log2-domain exponent
                     const float alpha = fminf(ALPHA_MAX, c.y * ex2_approx(e2));
-                    bool ok = !done && e2 <= 0.f && alpha >= ALPHA_MIN;
-                    const float test_T = T * (1.f - alpha);
-                    const bool stop = ok && test_T < T_STOP;                           // this one is NOT applied
-                    done = done || stop;
-                    ok = ok && !stop;
-                    const float w = ok ? alpha * T : 0.f;
+                    const bool valid = e2 <= 0.f && alpha >= ALPHA_MIN;
+                    const float test_T = Tm * (1.f - alpha);
+                    const bool ok = valid && test_T >= T_STOP;      // !ok on a valid splat = the stop (NOT applied)
+                    const float w = ok ? alpha * Tm : 0.f;
                     C0 = fmaf(col.x, w, C0);
                     C1 = fmaf(col.y, w, C1);
                     C2 = fmaf(col.z, w, C2);
                     Dp = fmaf(c.z, w, Dp);
                     Ac += w;
                     T = ok ? test_T : T;
+                    Tm = valid ? (ok ? test_T : 0.f) : Tm;
                     last = ok ? idxh + bit : last;
                     if (++since_check == 8) {                                          // warp-wide saturation test
                         since_check = 0;
-                        if (__all_sync(0xffffffffu, done)) { warp_done = true; break; }
+                        if (__all_sync(0xffffffffu, Tm == 0.f)) { warp_done = true; break; }
                     }
                 }
             }
-            if (!warp_done && __all_sync(0xffffffffu, done)) warp_done = true;
+            if (!warp_done && __all_sync(0xffffffffu, Tm == 0.f)) warp_done = true;
             if (warp_done && lane == 0) atomicAdd(&S.done_warps, 1u);
         }
         __syncwarp();
