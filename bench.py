@@ -308,7 +308,6 @@ def main():
     # host side of the end-to-end loop: 8-bit frames and packed cameras in pinned memory, as a dataloader would hold them
     gt_pinned = [u.pin_memory() for u in make_scene.gts_u8]
     cam_pinned_pack = [pack_cam(c).contiguous().pin_memory() for c in cams_cpu]
-    cam_stage = [torch.zeros(35).pin_memory() for _ in range(NS)]     # the graph's H2D node reads these
     loss_host = torch.zeros(NS).pin_memory()
     copy_stream = torch.cuda.Stream(device=dev)
     slot_camobj = []
@@ -337,18 +336,13 @@ def main():
         slot_loss[k].copy_(loss.detach().reshape(1))
 
     def e2e_body(k):
-        """The end-to-end step as ONE graph: compute on slot k (8-bit GT read directly by the L1 kernels) while a forked
-        branch copies step i+1's inputs -- 8-bit frame and packed camera, from pinned host memory -- into slot k+1; the
-        step's loss goes back to pinned host memory.  Slot k+1 is free: the step that used it ran earlier on this stream."""
-        cur = torch.cuda.current_stream()
-        copy_stream.wait_stream(cur)
-        with torch.cuda.stream(copy_stream):
-            kn = (k + 1) % NS
-            slot_u8[kn].copy_(gt_pinned[kn % 2], non_blocking=True)
-            slot_campack[kn].copy_(cam_stage[kn], non_blocking=True)
+        """The end-to-end step on slot k as one graph: compute (8-bit GT read directly by the L1 kernels) + the D2H copy of
+        the step's loss into pinned host memory.  The H2D copies of the inputs are issued eagerly, two steps ahead, on
+        the copy stream (e2e_run): with 8 ranks sharing the host's PCIe / memory system a copy can take longer than one
+        step, and a copy captured inside the graph would put that jitter on every rank's critical path (the ranks meet
+        at the exchange barriers every step)."""
         slot_body(k, True)
         loss_host[k:k + 1].copy_(slot_loss[k], non_blocking=True)
-        cur.wait_stream(copy_stream)
 
     def exchanges_behind_graph():
         """'around' mode: both exchanges right behind the replayed step; the SH block runs on the side stream and the
@@ -470,11 +464,10 @@ def main():
     # ---------------- end-to-end through the public API with host buffers: `e2e` ----------------
     h2d = gt_pinned[0].numel() * 1 + 35 * 4
 
-    # Graph mode: every replay holds the step's compute AND, on a forked branch, the H2D copy of step i+1's inputs from
-    # pinned host memory (what a pinned-memory DataLoader with non_blocking copies gives the reference), plus the D2H
-    # copy of the step's loss.  The host stages the next camera into the pinned staging buffer, replays, and reads the
-    # loss of step i-2 -- every copy and every read happens inside the timed region.  Eager mode: the same pipeline with
-    # explicit streams / events.
+    # The H2D copies of step i+2's inputs (8-bit frame + packed camera, pinned host memory -> the slot's device buffers)
+    # are issued on a copy stream while steps i and i+1 compute -- what a pinned-memory DataLoader with non_blocking copies
+    # and a prefetch depth of 2 gives the reference; graph mode replays compute + the D2H copy of the loss as one launch.
+    # The host reads the loss of step i-3.  Every copy and every read happens inside the timed region.
     ready = [torch.cuda.Event() for _ in range(NS)]
     done = [torch.cuda.Event() for _ in range(NS)]
 
@@ -489,20 +482,22 @@ def main():
         vals = []
         cur = torch.cuda.current_stream()
         if graphs is not None:
-            cam_stage[0].copy_(cam_pinned_pack[rank % N_CAMS])
-            slot_u8[0].copy_(gt_pinned[0], non_blocking=True)              # step 0's inputs (later ones: inside the graphs)
-            slot_campack[0].copy_(cam_stage[0], non_blocking=True)
-            L = NS - 1
+            L = NS - 1                                                      # the loss of step i-L is read at step i
+            prefetch(0)
+            prefetch(1)
             for i in range(n):
                 k = i % NS
-                if i >= L:                                                  # read step i-L's loss: L steps stay queued
+                if i >= L:
                     j = (i - L) % NS
                     tw = time.perf_counter()
                     done[j].synchronize()
                     e2e_run.wait_s += time.perf_counter() - tw
                     vals.append(float(loss_host[j]))
-                # next camera -> staging buffer k+1 (its previous reader, replay i-L, has completed: synchronised above)
-                cam_stage[(k + 1) % NS].copy_(cam_pinned_pack[((i + 1) * world + rank) % N_CAMS])
+                if i + 2 < n:                                               # inputs of step i+2 -> slot (i+2)%NS, free once
+                    if i + 2 >= NS:                                         # step i+2-NS (= i-2) has finished on the GPU
+                        copy_stream.wait_event(done[(i + 2) % NS])
+                    prefetch(i + 2)
+                cur.wait_event(ready[k])
                 graphs_u8[k].replay()
                 if around:
                     exchanges_behind_graph()
@@ -716,7 +711,7 @@ def main():
                     "what": "pinned-host 8-bit GT frame + camera matrices copied H2D every step (copy stream, overlapping the "
                             "previous step's compute), dequantised inside the fused L1 kernels, public GaussianRasterizer API fwd + fused "
                             "L1 + bwd (CUDA-graph replay of that call sequence unless --eager), every step's loss copied D2H "
-                            "(async, read three steps later); in graph mode copies and compute of a step are one graph launch; wall clock, max over ranks",
+                            "(async, read three steps later); H2D issued two steps ahead on a copy stream; wall clock, max over ranks",
                     "steps": e_steps, "h2d_gbs_measured": h2d_gbs, "h2d_gbs_min_over_ranks": h2d_gbs_min,
                     "host_numa_binding": numa_note},
             "roofline": roofline}
