@@ -17,12 +17,12 @@
 //  exchange got SLOWER, 0.218-0.237 ms vs 0.2045 ms for 70.8 MB, and the step 0.82 vs 0.72 ms: the in-switch reduction
 //  saturates at ~350 GB/s algorithmic with ~45 blocks in flight, and a wider grid only takes SM slots from the compute
 //  kernels the deferred block overlaps with.)
+#include <cstdlib>
 #include "common.cuh"
 
 namespace gg {
 
 constexpr int AR_THREADS = 512;
-constexpr int AR_UNROLL = 8;
 
 __device__ __forceinline__ uint32_t cas_sys_relaxed(uint32_t* a, uint32_t cmp, uint32_t val) {
     uint32_t old;
@@ -58,6 +58,7 @@ __device__ __forceinline__ void cross_rank_barrier(uint32_t* const* __restrict__
     }
 }
 
+template <int AR_UNROLL>
 __global__ void __launch_bounds__(AR_THREADS)
 nvls_allreduce_kernel(float* __restrict__ mc, uint32_t* const* __restrict__ pads, int rank, int world, int slot0,
                       int64_t n_vec4, float scale) {
@@ -124,7 +125,10 @@ int launch_gate_signal(uint32_t* gate, cudaStream_t s) {
 int launch_nvls_allreduce(float* mc, uint32_t* const* pads, int rank, int world, int slot0, int64_t n_vec4, float scale,
                           int blocks, cudaStream_t s) {
     if (n_vec4 <= 0) return 0;
-    nvls_allreduce_kernel<<<blocks, AR_THREADS, 0, s>>>(mc, pads, rank, world, slot0, n_vec4, scale);
+    // independent 16-byte reductions in flight per thread: 8 by default; GG_AR_UNROLL=16 doubles the bytes in flight
+    static const int unroll = []() { const char* e = getenv("GG_AR_UNROLL"); return (e && atoi(e) == 16) ? 16 : 8; }();
+    if (unroll == 16) nvls_allreduce_kernel<16><<<blocks, AR_THREADS, 0, s>>>(mc, pads, rank, world, slot0, n_vec4, scale);
+    else nvls_allreduce_kernel<8><<<blocks, AR_THREADS, 0, s>>>(mc, pads, rank, world, slot0, n_vec4, scale);
     return 1;
 }
 
