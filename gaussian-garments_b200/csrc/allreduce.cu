@@ -125,8 +125,9 @@ int launch_gate_signal(uint32_t* gate, cudaStream_t s) {
 int launch_nvls_allreduce(float* mc, uint32_t* const* pads, int rank, int world, int slot0, int64_t n_vec4, float scale,
                           int blocks, cudaStream_t s) {
     if (n_vec4 <= 0) return 0;
-    // independent 16-byte reductions in flight per thread: 8 by default; GG_AR_UNROLL=16 doubles the bytes in flight
-    static const int unroll = []() { const char* e = getenv("GG_AR_UNROLL"); return (e && atoi(e) == 16) ? 16 : 8; }();
+    // independent 16-byte reductions in flight per thread: 16 by default (8 x B200, cfg2 step: 0.683 ms vs 0.696 ms with
+    // 8; exchange alone 0.275 vs 0.286 ms); GG_AR_UNROLL=8 selects the smaller variant
+    static const int unroll = []() { const char* e = getenv("GG_AR_UNROLL"); return (e && atoi(e) == 8) ? 8 : 16; }();
     if (unroll == 16) nvls_allreduce_kernel<16><<<blocks, AR_THREADS, 0, s>>>(mc, pads, rank, world, slot0, n_vec4, scale);
     else nvls_allreduce_kernel<8><<<blocks, AR_THREADS, 0, s>>>(mc, pads, rank, world, slot0, n_vec4, scale);
     return 1;
