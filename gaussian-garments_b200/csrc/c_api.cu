@@ -1,6 +1,7 @@
 // c_api.cu -- extern "C" boundary (include/gg_raster.h).  Argument validation, workspace
-// carving, launch sequencing, error reporting.  No allocation.  The only process-wide state is diagnostic: the launch
-// counter and the optional per-kernel timing events (off by default); the compute path itself is re-entrant.
+// carving, launch sequencing, error reporting.  No device-memory allocation.  Process-wide state: the launch counter and
+// the optional per-kernel timing events (diagnostic, off by default), environment switches read once, and the forward's
+// fork sets (a side stream + two events per (device, caller stream), see ForkSet); the compute path is re-entrant.
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>

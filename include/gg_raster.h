@@ -17,9 +17,10 @@
  *   - every function returns 0 on success, a positive cudaError_t value or a negative GG_E_*
  *     code on failure; gg_last_error() returns a thread-local description.  Nothing throws or
  *     exits across the boundary.
- *   - re-entrant; the only process-wide state is diagnostic (launch counter, optional per-kernel timing events, both off
- *     the compute path); `device` is re-asserted with cudaSetDevice because
- *     autograd calls backward on a worker thread (SURVEY.md 8b "Threading / streams").
+ *   - re-entrant.  Process-wide state: diagnostics (launch counter, optional per-kernel timing events, off the compute
+ *     path), environment switches read once, and the forward's fork sets -- one {side stream, two events} per
+ *     (device, caller stream), mutex-protected (see gg_forward_color).  `device` is re-asserted with cudaSetDevice
+ *     because autograd calls backward on a worker thread (SURVEY.md 8b "Threading / streams").
  *   - all floating tensors are fp32, contiguous, 16-byte aligned base pointers.
  */
 #ifndef GG_RASTER_H_
