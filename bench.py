@@ -658,13 +658,14 @@ def main():
     K = int(sum(Ks) / len(Ks))
     gx, gy = (W + 15) // 16, (H + 15) // 16
     ab = algorithmic_bytes(args.gaussians, K, W * H, gx * gy)
-    traffic, ncu_issue, traffic_src = {}, {}, None
+    traffic, ncu_issue, ncu_winstr, traffic_src = {}, {}, {}, None
     try:   # per-launch dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture (profiles/): STATIC
         tpath = next(p for p in ("r2_ncu_traffic.json", "r1_ncu_traffic.json") if os.path.exists(os.path.join(ROOT, "profiles", p)))
         traffic_src = f"static: profiles/{tpath} (ncu --set full capture of this command, not measured in this run)"
         tj = json.load(open(os.path.join(ROOT, "profiles", tpath)))
         traffic = {k: int(v["traffic"]) for k, v in tj["kernels"].items()}
         ncu_issue = {k: v.get("ncu_issue_slot_pct") for k, v in tj["kernels"].items()}
+        ncu_winstr = {k: v.get("warp_instructions") for k, v in tj["kernels"].items()}
     except Exception:
         pass
     kernels = []
@@ -677,13 +678,28 @@ def main():
                         "ncu_issue_slot_pct": ncu_issue.get(name)})
     dom = kernels[0]
     interactions = 256 * K
+    # the issue pipe is the honest ceiling of the blend kernels: warp instructions per launch (STATIC, from the committed
+    # ncu capture) over the live launch time, against 4 warp-instructions per cycle per SM at the sampled SM clock
+    issue = None
+    try:
+        wi = float(ncu_winstr.get(dom["kernel"]) or 0.0)
+        props = torch.cuda.get_device_properties(dev)
+        mhz = float(clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 0.0)
+        if wi > 0 and mhz > 0:
+            peak_wips = props.multi_processor_count * 4 * mhz * 1e6
+            ach = wi / (dom["ms"] * 1e-3)
+            issue = {"warp_instructions_per_launch_static": int(wi), "achieved_gwarp_instr_s": round(ach / 1e9, 1),
+                     "peak_gwarp_instr_s": round(peak_wips / 1e9, 1), "frac": round(ach / peak_wips, 3),
+                     "thread_instr_per_pixel_gaussian_pair": round(wi * 32.0 / max(1, interactions), 2)}
+    except Exception:
+        issue = None
     roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_gbs"], "peak": peak_gbs, "unit": "GB/s",
                 "frac": dom["frac"], "traffic": dom["traffic"], "peak_source": peak_src, "avg_launch_ms": dom["ms"],
                 "num_rendered": K, "pixel_gaussian_pairs": interactions,
                 "note": "blend kernels are instruction-issue bound by construction (256*K pixel-Gaussian pairs >> their "
-                        "bytes): ncu issue-slot utilisation 64-69 % at ~1-3 % DRAM (`ncu_issue_slot_pct`, from the committed "
+                        "bytes): ncu issue-slot utilisation 70-84 % at 3-5 % DRAM (`ncu_issue_slot_pct`, `issue_roofline`; static, from the committed "
                         "capture); the streaming kernels (preprocess_bwd, sh_color, photometric) carry the HBM claim",
-                "ncu_issue_slot_pct": ncu_issue.get(dom["kernel"]), "traffic_source": traffic_src,
+                "ncu_issue_slot_pct": ncu_issue.get(dom["kernel"]), "issue_roofline": issue, "traffic_source": traffic_src,
                 "kernels": kernels, "kernel_ms_sum": round(sum(k["ms"] for k in kernels), 4)}
 
     cpu_baseline = None
